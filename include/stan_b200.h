@@ -1,0 +1,168 @@
+/*
+ * stan_b200.h — C ABI of libstan_b200.so, the B200-native replacement for the body of
+ * Solver.SolverLinearStatics in galuszkm/STAN (src/STAN_Solver/Solver.cs:97-210).
+ *
+ * The reference has no FFI: its seams are managed calls.  Each entry point below names the
+ * managed code it replaces; INTEGRATION.md shows the P/Invoke stub (interop/StanNative.cs)
+ * and the patch to SolverLinearStatics.  Plain pointers and sizes only; every array argument
+ * is owned by the caller and is copied before the call returns (P/Invoke pins blittable
+ * arrays only for the duration of a call).  All functions return 0 on success or a negative
+ * STAN_E_* code; stan_last_error() gives a thread-local message.  No exceptions cross the ABI.
+ * cdecl, x86-64, not re-entrant per handle; one handle drives one GPU.
+ *
+ * Flat model = the reference's object graph in dictionary insertion order
+ * (SURVEY.md §8a R6): node i is the i-th entry of Database.NodeLib, element e the e-th entry
+ * of Database.ElemLib, connectivity holds 0-based node positions in CHEXA order
+ * (src/STAN_Database/FE_Library.cs:108-115).
+ */
+#ifndef STAN_B200_H
+#define STAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define STAN_OK            0
+#define STAN_E_ARG        -1  /* bad argument / out-of-range index */
+#define STAN_E_CUDA       -2  /* CUDA runtime failure (message has the detail) */
+#define STAN_E_SINGULAR   -3  /* Jacobian determinant == 0 (MatrixST.cs:298,317 throws) */
+#define STAN_E_STATE      -4  /* call order violated (e.g. solve before assemble) */
+#define STAN_E_CAPACITY   -5  /* a node couples to more nodes than STAN_MAX_ROW_BLOCKS */
+#define STAN_E_DOFMAP     -6  /* AssignDOF failed: no start node / disconnected mesh (Database.cs:178-196, :218) */
+#define STAN_E_COMM       -7  /* NCCL / multi-GPU failure */
+
+#define STAN_HEX8_G1 1        /* Element.Type "HEX8_G1", FE_Library.cs:63-89 */
+#define STAN_HEX8_G2 2        /* Element.Type "HEX8_G2", FE_Library.cs:91-131 */
+
+#define STAN_MAX_ROW_BLOCKS 96
+
+typedef struct stan_handle stan_handle;
+
+typedef struct {
+    int32_t device;            /* CUDA ordinal; -1 = current device */
+    int32_t rank;              /* this process's partition, 0 <= rank < world */
+    int32_t world;             /* number of partitions (GPUs); 1 = single GPU */
+    int32_t flags;             /* reserved, 0 */
+} stan_options;
+
+/* Mirrors Analysis.LinSolverTolerance / LinSolverIterMax (Analysis.cs:10-11) plus the ALGLIB
+ * lincg internals that LinearSolver_CG leaves at their defaults (SolverFunctions.cs:270-330). */
+typedef struct {
+    double  epsf;              /* lincgsetcond EpsF: stop when ||r||2 <= epsf*||b||2; (0,0) -> 1e-6 */
+    int32_t maxits;            /* lincgsetcond MaxIts; 0 = unlimited */
+    int32_t its_before_rupdate;/* true-residual refresh period, ALGLIB default 10; 0 = never */
+    int32_t its_before_restart;/* direction restart period, ALGLIB default n (pass 0) */
+    int32_t merit_check;       /* 1 = ALGLIB: terminationtype 7 when the energy functional stalls */
+    int32_t zero_based_counter;/* 0 = period tests on k = 1,2,..; 1 = on k-1 */
+    int32_t time_kernels;      /* 1 = bracket every SpMV launch with CUDA events (no graph replay) */
+    int32_t reserved;
+} stan_cg_options;
+
+/* alglib.lincgreport as consumed at SolverFunctions.cs:305-327, plus device timings. */
+typedef struct {
+    int32_t terminationtype;   /* 1, 5, 7, -4, -5 (SolverFunctions.cs:311-319) */
+    int32_t iterationscount;
+    int32_t nmv;               /* matrix-vector products counted as ALGLIB does (incl. r0 = b - A*0) */
+    int32_t spmv_launches;     /* SpMV kernels actually launched by this rank */
+    double  r2;                /* squared 2-norm of the final residual */
+    double  bnorm;             /* ||b||2 */
+    double  solve_ms;          /* device time of the whole solve (CUDA events) */
+    double  spmv_ms;           /* summed device time of the SpMV launches (time_kernels = 1), else 0 */
+    int64_t spmv_bytes;        /* algorithmic bytes one SpMV launch moves on this rank */
+    int64_t iter_bytes;        /* algorithmic bytes of one full CG iteration on this rank */
+    int64_t kernel_launches;   /* all kernels launched by the solve */
+} stan_cg_report;
+
+typedef struct {
+    int64_t n_dof;             /* 3 * n_nodes (Database.nDOF) */
+    int64_t n_fixed;           /* |Distinct(Fix_DOF)| (Solver.cs:117) */
+    int64_t n_rows_local;      /* block rows (nodes) owned by this rank */
+    int64_t n_blocks_local;    /* stored 3x3 blocks on this rank */
+    int64_t nnz_upper;         /* entries of the reference's upper-triangle CRS (global) */
+    int64_t assembly_bytes;    /* algorithmic bytes of the assembly kernel */
+    double  assembly_flops;    /* algorithmic flops of the element integration */
+    double  pattern_ms;        /* incidence + block pattern build */
+    double  assembly_ms;       /* hex8 integration + deterministic row assembly kernel */
+    double  total_ms;          /* whole stan_assemble call on the device */
+    int64_t kernel_launches;
+} stan_assembly_stats;
+
+typedef struct {
+    double  recover_ms;
+    int64_t recover_bytes;     /* algorithmic bytes */
+    int64_t kernel_launches;
+} stan_recovery_stats;
+
+const char *stan_last_error(void);
+int stan_version(void);
+
+int stan_create(const stan_options *opts, stan_handle **out);
+int stan_destroy(stan_handle *h);
+
+/* --- model upload: replaces the object-graph reads of Solver.cs:81-152 --------------------- */
+/* Node.X/Y/Z (Node.cs:12-14), Element.NList/Type/MatID (Element.cs:15-18). */
+int stan_set_mesh(stan_handle *h, int64_t n_nodes, const double *xyz, int64_t n_elem, const int32_t *conn,
+                  const uint8_t *elem_type, const int32_t *elem_mat);
+/* Material.SetElastic(E, Poisson) for every "Elastic" material (Solver.cs:33-39, Material.cs:31-56). */
+int stan_set_materials(stan_handle *h, int32_t n_mat, const double *E, const double *nu);
+/* Node.DOF[0]/3 per node when the managed side already ran Database.AssignDOF (Solver.cs:46). */
+int stan_set_dof_map(stan_handle *h, const int32_t *node_index);
+/* Native Database.AssignDOF (Database.cs:140-234): computes, stores and returns the BFS index. */
+int stan_assign_dof(stan_handle *h, int32_t *node_index_out);
+/* BCLib entries of Type "SPC": a DOF is fixed iff its value == 1 (Solver.cs:106-114). */
+int stan_set_spc(stan_handle *h, int64_t n, const int32_t *node, const double *val3);
+/* BCLib entries of Type "PointLoad", accumulated in list order (Solver.cs:136-152). */
+int stan_set_loads(stan_handle *h, int64_t n, const int32_t *node, const double *fxyz);
+
+/* --- the hot path ------------------------------------------------------------------------- */
+/* Fun.ParallelAssembly_K(DB, nDOF_reduction, 1, "Initial") + nDOF_reduction + F
+ * (Solver.cs:104-156, SolverFunctions.cs:117-180, Element.cs:118-155). */
+int stan_assemble(stan_handle *h, stan_assembly_stats *stats);
+/* Fun.LinearSolver_CG(K, F, AnalysisLib) (Solver.cs:162, SolverFunctions.cs:270-330). */
+int stan_solve_cg(stan_handle *h, const stan_cg_options *opts, stan_cg_report *report);
+/* Include_BC_DOF + dU_buffer + Elem.Recovery_Stress + Update_StrainStress
+ * (Solver.cs:168-210, Element.cs:211-246, 257-267). */
+int stan_recover(stan_handle *h, stan_recovery_stats *stats);
+
+/* --- results: what Solver.cs:171-178,203-210 writes back into Node / Element --------------- */
+/* U_Full[nDOF] indexed by DOF (zeros at fixed DOFs). */
+int stan_get_displacements(stan_handle *h, double *u_full);
+/* Element.Strain[1] / Stress[1]: n_elem x 8 x 6 row-major each. */
+int stan_get_strain_stress(stan_handle *h, double *strain, double *stress);
+
+/* --- parity / inspection (SURVEY §8b "optional") ------------------------------------------- */
+int stan_get_dof_reduction(stan_handle *h, int32_t *ndof_reduction);          /* Solver.cs:121-132 */
+int stan_get_rhs(stan_handle *h, double *F_reduced);                          /* Solver.cs:136-152 */
+int stan_get_solution_reduced(stan_handle *h, double *U_reduced);             /* Exclude_BC_DOF(U_Full) */
+/* Reduced upper-triangle CRS as alglib.sparseconverttocrs leaves it (structural pattern). */
+int stan_get_csr_upper_size(stan_handle *h, int64_t *n, int64_t *nnz);
+int stan_get_csr_upper(stan_handle *h, int64_t *rowptr, int32_t *col, double *val);
+/* Element.K_Initial for elements [first, first+count): count x 24 x 24 row-major. */
+int stan_element_stiffness(stan_handle *h, int64_t first, int64_t count, double *ke);
+/* y = K x on the stored matrix, x and y in full DOF space (fixed DOFs act as identity rows). */
+int stan_spmv(stan_handle *h, const double *x_full, double *y_full);
+/* Device time of `reps` back-to-back SpMV launches on the assembled matrix (CUDA events). */
+int stan_time_spmv(stan_handle *h, int32_t reps, double *ms_per_launch, int64_t *bytes_per_launch);
+
+/* Kernels launched through this handle so far (bench.py's gpu_launches). */
+int64_t stan_kernel_launches(stan_handle *h);
+
+/* --- multi-GPU (one process per GPU) ------------------------------------------- */
+/* Rank 0 creates the 128-byte NCCL id, the host side broadcasts it, every rank joins. */
+int stan_comm_unique_id(void *id128);
+int stan_comm_init(stan_handle *h, const void *id128);
+/* Row range [first, last) of BFS nodes owned by this rank after stan_assemble. */
+int stan_get_partition(stan_handle *h, int64_t *first_row, int64_t *last_row);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* STAN_B200_H */

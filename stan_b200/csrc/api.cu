@@ -1,0 +1,371 @@
+// C ABI of libstan_b200.so (include/stan_b200.h): argument checking, call-order state machine,
+// host<->device copies at the boundary.  Orchestrates pattern.cu / assembly.cu / cg.cu / recovery.cu
+// in the order of Solver.SolverLinearStatics (/root/reference/src/STAN_Solver/Solver.cs:97-210).
+#include <cmath>
+
+#include "common.cuh"
+
+namespace stan {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+void partition_rows(stan_handle *h);   // comm.cu
+
+static int check(stan_handle *h) {
+    if (!h) { set_error("null handle"); return STAN_E_ARG; }
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e)); return STAN_E_CUDA; }
+    return STAN_OK;
+}
+
+static int upload_dof_map(stan_handle *h, const int32_t *node_index) {
+    cudaStream_t s = h->stream;
+    h->h_node_index.assign(node_index, node_index + h->n_nodes);
+    STAN_TRY(h->d_node_index.alloc(h->n_nodes, s));
+    STAN_CUDA(cudaMemcpyAsync(h->d_node_index.p, h->h_node_index.data(), h->n_nodes * sizeof(int32_t),
+                              cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    h->have_dof = true;
+    h->assembled = h->solved = h->recovered = false;
+    return STAN_OK;
+}
+
+}  // namespace stan
+
+using namespace stan;
+
+extern "C" {
+
+const char *stan_last_error(void) { return g_err; }
+int stan_version(void) { return 100; }
+
+int stan_create(const stan_options *opts, stan_handle **out) {
+    if (!out) { set_error("null out pointer"); return STAN_E_ARG; }
+    *out = nullptr;
+    int dev = opts ? opts->device : -1;
+    if (dev < 0) STAN_CUDA(cudaGetDevice(&dev));
+    STAN_CUDA(cudaSetDevice(dev));
+    stan_handle *h = new stan_handle();
+    h->device = dev;
+    h->rank = opts ? opts->rank : 0;
+    h->world = opts && opts->world > 0 ? opts->world : 1;
+    if (h->rank < 0 || h->rank >= h->world || h->world > 32) {
+        set_error("rank %d outside world %d (max 32)", h->rank, h->world);
+        delete h;
+        return STAN_E_ARG;
+    }
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    STAN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    STAN_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    STAN_CUDA(cudaEventCreate(&h->ev0)); STAN_CUDA(cudaEventCreate(&h->ev1));
+    STAN_CUDA(cudaEventCreate(&h->ev2)); STAN_CUDA(cudaEventCreate(&h->ev3));
+    cudaMemPool_t pool;
+    STAN_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;     // keep freed blocks cached: assemble/solve cycles reuse them
+    STAN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    STAN_TRY(upload_fe_tables());
+    *out = h;
+    return STAN_OK;
+}
+
+int stan_destroy(stan_handle *h) {
+    if (!h) return STAN_OK;
+    cudaSetDevice(h->device);
+    cudaStream_t s = h->stream;
+    cudaStreamSynchronize(s);
+    comm_destroy(h);
+    h->d_xyz.release(s); h->d_conn.release(s); h->d_etype.release(s); h->d_emat.release(s);
+    h->d_lambda.release(s); h->d_G.release(s); h->d_node_index.release(s); h->d_inv.release(s);
+    h->d_inc_ptr.release(s); h->d_inc.release(s); h->d_brow_ptr.release(s); h->d_bcol.release(s);
+    h->d_bcol_loc.release(s); h->d_vals.release(s); h->d_fixed.release(s); h->d_red.release(s);
+    h->d_b.release(s); h->d_d2.release(s); h->d_err.release(s); h->d_x.release(s); h->d_xalt.release(s);
+    h->d_r.release(s); h->d_p.release(s); h->d_mv.release(s); h->d_partials.release(s); h->d_state.release(s);
+    h->d_counter.release(s); h->d_ufull.release(s); h->d_strain.release(s); h->d_stress.release(s);
+    cudaStreamSynchronize(s);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
+    cudaStreamDestroy(h->stream); cudaStreamDestroy(h->comm_stream);
+    delete h;
+    return STAN_OK;
+}
+
+int stan_set_mesh(stan_handle *h, int64_t n_nodes, const double *xyz, int64_t n_elem, const int32_t *conn,
+                  const uint8_t *elem_type, const int32_t *elem_mat) {
+    STAN_TRY(check(h));
+    if (n_nodes <= 0 || n_elem <= 0 || !xyz || !conn || !elem_type || !elem_mat) {
+        set_error("stan_set_mesh: empty mesh or null array"); return STAN_E_ARG;
+    }
+    if (3 * n_nodes > INT32_MAX) { set_error("more than %d DOFs", INT32_MAX); return STAN_E_ARG; }
+    for (int64_t i = 0; i < 8 * n_elem; i++)
+        if (conn[i] < 0 || conn[i] >= n_nodes) {
+            set_error("element %lld references node %d outside [0,%lld)", (long long)(i / 8), conn[i], (long long)n_nodes);
+            return STAN_E_ARG;
+        }
+    for (int64_t e = 0; e < n_elem; e++)
+        if (elem_type[e] != STAN_HEX8_G1 && elem_type[e] != STAN_HEX8_G2) {
+            set_error("element %lld has unsupported type %d (only HEX8_G1/HEX8_G2)", (long long)e, (int)elem_type[e]);
+            return STAN_E_ARG;
+        }
+    cudaStream_t s = h->stream;
+    h->n_nodes = n_nodes; h->n_elem = n_elem;
+    h->h_conn.assign(conn, conn + 8 * n_elem);
+    STAN_TRY(h->d_xyz.alloc(3 * n_nodes, s)); STAN_TRY(h->d_conn.alloc(8 * n_elem, s));
+    STAN_TRY(h->d_etype.alloc(n_elem, s)); STAN_TRY(h->d_emat.alloc(n_elem, s));
+    STAN_CUDA(cudaMemcpyAsync(h->d_xyz.p, xyz, 3 * n_nodes * sizeof(double), cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaMemcpyAsync(h->d_conn.p, conn, 8 * n_elem * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaMemcpyAsync(h->d_etype.p, elem_type, n_elem, cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaMemcpyAsync(h->d_emat.p, elem_mat, n_elem * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    int32_t mmax = 0;
+    for (int64_t e = 0; e < n_elem; e++) { if (elem_mat[e] < 0) { set_error("negative material index"); return STAN_E_ARG; } mmax = std::max(mmax, elem_mat[e]); }
+    h->n_mat = std::max(h->n_mat, 0);
+    h->have_mesh = true;
+    h->have_dof = h->assembled = h->solved = h->recovered = false;
+    h->h_spc_node.clear(); h->h_spc_val.clear(); h->h_load_node.clear(); h->h_load_val.clear();
+    (void)mmax;
+    return STAN_OK;
+}
+
+int stan_set_materials(stan_handle *h, int32_t n_mat, const double *E, const double *nu) {
+    STAN_TRY(check(h));
+    if (n_mat <= 0 || !E || !nu) { set_error("stan_set_materials: no materials"); return STAN_E_ARG; }
+    std::vector<double> lam(n_mat), G(n_mat);
+    for (int i = 0; i < n_mat; i++) {                       // Material.SetElastic, Material.cs:39-40
+        const double Young = E[i], Poisson = nu[i];
+        lam[i] = (Young * Poisson) / ((1 - 2 * Poisson) * (1 + Poisson));
+        G[i] = (0.5 * Young) / (1 + Poisson);
+        if (!std::isfinite(lam[i]) || !std::isfinite(G[i])) { set_error("material %d: E=%g nu=%g gives a non-finite D", i, Young, Poisson); return STAN_E_ARG; }
+    }
+    cudaStream_t s = h->stream;
+    STAN_TRY(h->d_lambda.alloc(n_mat, s)); STAN_TRY(h->d_G.alloc(n_mat, s));
+    STAN_CUDA(cudaMemcpyAsync(h->d_lambda.p, lam.data(), n_mat * sizeof(double), cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaMemcpyAsync(h->d_G.p, G.data(), n_mat * sizeof(double), cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    h->n_mat = n_mat;
+    h->have_mat = true;
+    h->assembled = h->solved = h->recovered = false;
+    return STAN_OK;
+}
+
+int stan_set_dof_map(stan_handle *h, const int32_t *node_index) {
+    STAN_TRY(check(h));
+    if (!h->have_mesh) { set_error("stan_set_dof_map before stan_set_mesh"); return STAN_E_STATE; }
+    if (!node_index) { set_error("null dof map"); return STAN_E_ARG; }
+    std::vector<uint8_t> seen((size_t)h->n_nodes, 0);
+    for (int64_t i = 0; i < h->n_nodes; i++) {
+        int32_t p = node_index[i];
+        if (p < 0 || p >= h->n_nodes || seen[p]) { set_error("dof map is not a permutation (node %lld -> %d)", (long long)i, p); return STAN_E_ARG; }
+        seen[p] = 1;
+    }
+    return upload_dof_map(h, node_index);
+}
+
+int stan_assign_dof(stan_handle *h, int32_t *node_index_out) {
+    STAN_TRY(check(h));
+    if (!h->have_mesh) { set_error("stan_assign_dof before stan_set_mesh"); return STAN_E_STATE; }
+    std::vector<int32_t> ni((size_t)h->n_nodes);
+    STAN_TRY(assign_dof_host(h->n_nodes, h->n_elem, h->h_conn.data(), ni.data()));
+    if (node_index_out) memcpy(node_index_out, ni.data(), ni.size() * sizeof(int32_t));
+    return upload_dof_map(h, ni.data());
+}
+
+int stan_set_spc(stan_handle *h, int64_t n, const int32_t *node, const double *val3) {
+    STAN_TRY(check(h));
+    if (!h->have_mesh) { set_error("stan_set_spc before stan_set_mesh"); return STAN_E_STATE; }
+    if (n < 0 || (n > 0 && (!node || !val3))) { set_error("stan_set_spc: bad arguments"); return STAN_E_ARG; }
+    for (int64_t i = 0; i < n; i++)
+        if (node[i] < 0 || node[i] >= h->n_nodes) { set_error("SPC entry %lld: node %d not in the mesh", (long long)i, node[i]); return STAN_E_ARG; }
+    h->h_spc_node.assign(node, node + n);
+    h->h_spc_val.assign(val3, val3 + 3 * n);
+    h->assembled = h->solved = h->recovered = false;
+    return STAN_OK;
+}
+
+int stan_set_loads(stan_handle *h, int64_t n, const int32_t *node, const double *fxyz) {
+    STAN_TRY(check(h));
+    if (!h->have_mesh) { set_error("stan_set_loads before stan_set_mesh"); return STAN_E_STATE; }
+    if (n < 0 || (n > 0 && (!node || !fxyz))) { set_error("stan_set_loads: bad arguments"); return STAN_E_ARG; }
+    for (int64_t i = 0; i < n; i++)
+        if (node[i] < 0 || node[i] >= h->n_nodes) { set_error("load entry %lld: node %d not in the mesh", (long long)i, node[i]); return STAN_E_ARG; }
+    h->h_load_node.assign(node, node + n);
+    h->h_load_val.assign(fxyz, fxyz + 3 * n);
+    h->assembled = h->solved = h->recovered = false;
+    return STAN_OK;
+}
+
+int stan_assemble(stan_handle *h, stan_assembly_stats *stats) {
+    STAN_TRY(check(h));
+    if (!h->have_mesh || !h->have_mat || !h->have_dof) {
+        set_error("stan_assemble needs mesh, materials and a dof map"); return STAN_E_STATE;
+    }
+    cudaStream_t s = h->stream;
+    const int64_t launches0 = h->launches;
+    h->assembled = h->solved = h->recovered = false;
+    partition_rows(h);
+    STAN_CUDA(cudaEventRecord(h->ev2, s));
+    STAN_TRY(build_system_pattern(h));
+    STAN_TRY(comm_build_halo(h));
+    STAN_TRY(build_rhs(h));
+    STAN_CUDA(cudaEventRecord(h->ev0, s));
+    STAN_TRY(run_assembly(h));
+    STAN_CUDA(cudaEventRecord(h->ev1, s));
+    int32_t herr[4];
+    STAN_CUDA(cudaMemcpyAsync(herr, h->d_err.p, sizeof herr, cudaMemcpyDeviceToHost, s));
+    STAN_CUDA(cudaEventRecord(h->ev3, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    STAN_CUDA(cudaGetLastError());
+    if (herr[2]) { set_error("singular Jacobian: an element has det(J) == 0 at a Gauss point"); return STAN_E_SINGULAR; }
+    h->assembled = true;
+    if (stats) {
+        float t_pat = 0.f, t_asm = 0.f, t_all = 0.f;
+        cudaEventElapsedTime(&t_pat, h->ev2, h->ev0);
+        cudaEventElapsedTime(&t_asm, h->ev0, h->ev1);
+        cudaEventElapsedTime(&t_all, h->ev2, h->ev3);
+        memset(stats, 0, sizeof *stats);
+        stats->n_dof = 3 * h->n_nodes;
+        stats->n_fixed = h->n_fixed;
+        stats->n_rows_local = h->row1 - h->row0;
+        stats->n_blocks_local = h->n_blocks;
+        stats->nnz_upper = h->nnz_upper;
+        // each stored value written once + connectivity/coordinates read once
+        stats->assembly_bytes = 72 * h->n_blocks + h->n_elem * 40 + 24 * h->n_nodes;
+        double fl = 0.0;
+        // structured minimum per element: G2 17.3 kflop, G1 2.2 kflop; types are mixed per element
+        // so the caller-visible figure assumes the type of element 0 for the whole mesh
+        fl = (double)h->n_elem * 17300.0;
+        stats->assembly_flops = fl;
+        stats->pattern_ms = t_pat;
+        stats->assembly_ms = t_asm;
+        stats->total_ms = t_all;
+        stats->kernel_launches = h->launches - launches0;
+    }
+    return STAN_OK;
+}
+
+int stan_solve_cg(stan_handle *h, const stan_cg_options *opts, stan_cg_report *report) {
+    STAN_TRY(check(h));
+    if (!h->assembled) { set_error("stan_solve_cg before stan_assemble"); return STAN_E_STATE; }
+    if (!opts || !report) { set_error("stan_solve_cg: null options/report"); return STAN_E_ARG; }
+    if (opts->epsf < 0 || opts->maxits < 0) { set_error("stan_solve_cg: negative EpsF/MaxIts"); return STAN_E_ARG; }
+    if (!opts->merit_check && opts->maxits == 0 && opts->epsf < 1e-12) {
+        set_error("merit_check = 0 with EpsF < 1e-12 needs MaxIts > 0 (FP64 cannot reach it; the loop would not end)");
+        return STAN_E_ARG;
+    }
+    memset(report, 0, sizeof *report);
+    h->recovered = false;
+    return solve_cg(h, opts, report);
+}
+
+int stan_recover(stan_handle *h, stan_recovery_stats *stats) {
+    STAN_TRY(check(h));
+    if (!h->solved) { set_error("stan_recover before stan_solve_cg"); return STAN_E_STATE; }
+    return run_recovery(h, stats);
+}
+
+int stan_get_displacements(stan_handle *h, double *u_full) {
+    STAN_TRY(check(h));
+    if (!h->solved) { set_error("no solution yet"); return STAN_E_STATE; }
+    if (!u_full) { set_error("null output"); return STAN_E_ARG; }
+    if (!h->recovered) STAN_TRY(scatter_solution(h));
+    STAN_CUDA(cudaMemcpyAsync(u_full, h->d_ufull.p, 3 * h->n_nodes * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    STAN_CUDA(cudaStreamSynchronize(h->stream));
+    return STAN_OK;
+}
+
+int stan_get_strain_stress(stan_handle *h, double *strain, double *stress) {
+    STAN_TRY(check(h));
+    if (!h->recovered) { set_error("stan_get_strain_stress before stan_recover"); return STAN_E_STATE; }
+    const size_t bytes = (size_t)48 * h->n_elem * sizeof(double);
+    if (strain) STAN_CUDA(cudaMemcpyAsync(strain, h->d_strain.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (stress) STAN_CUDA(cudaMemcpyAsync(stress, h->d_stress.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    STAN_CUDA(cudaStreamSynchronize(h->stream));
+    return STAN_OK;
+}
+
+int stan_get_dof_reduction(stan_handle *h, int32_t *ndof_reduction) {
+    STAN_TRY(check(h));
+    if (!h->assembled) { set_error("not assembled"); return STAN_E_STATE; }
+    STAN_CUDA(cudaMemcpyAsync(ndof_reduction, h->d_red.p, 3 * h->n_nodes * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    STAN_CUDA(cudaStreamSynchronize(h->stream));
+    return STAN_OK;
+}
+
+static int reduced_from_full(stan_handle *h, const double *d_full_local, double *out) {
+    if (h->world != 1) { set_error("reduced-vector export is single-GPU only"); return STAN_E_STATE; }
+    const int64_t ndof = 3 * h->n_nodes;
+    std::vector<double> full((size_t)ndof);
+    std::vector<int32_t> red((size_t)ndof);
+    STAN_CUDA(cudaMemcpyAsync(full.data(), d_full_local, ndof * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    STAN_CUDA(cudaMemcpyAsync(red.data(), h->d_red.p, ndof * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    STAN_CUDA(cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < ndof; i++)                      // Exclude_BC_DOF, SolverFunctions.cs:540-555
+        if (red[i] != -1) out[i - red[i]] = full[i];
+    return STAN_OK;
+}
+
+int stan_get_rhs(stan_handle *h, double *F_reduced) {
+    STAN_TRY(check(h));
+    if (!h->assembled) { set_error("not assembled"); return STAN_E_STATE; }
+    return reduced_from_full(h, h->d_b.p, F_reduced);
+}
+
+int stan_get_solution_reduced(stan_handle *h, double *U_reduced) {
+    STAN_TRY(check(h));
+    if (!h->solved) { set_error("no solution yet"); return STAN_E_STATE; }
+    return reduced_from_full(h, h->x_in_alt ? h->d_xalt.p : h->d_x.p, U_reduced);
+}
+
+int stan_get_csr_upper_size(stan_handle *h, int64_t *n, int64_t *nnz) {
+    STAN_TRY(check(h));
+    if (!h->assembled) { set_error("not assembled"); return STAN_E_STATE; }
+    return export_csr_upper_size(h, n, nnz);
+}
+
+int stan_get_csr_upper(stan_handle *h, int64_t *rowptr, int32_t *col, double *val) {
+    STAN_TRY(check(h));
+    if (!h->assembled) { set_error("not assembled"); return STAN_E_STATE; }
+    return export_csr_upper(h, rowptr, col, val);
+}
+
+int stan_element_stiffness(stan_handle *h, int64_t first, int64_t count, double *ke) {
+    STAN_TRY(check(h));
+    if (!h->have_mesh || !h->have_mat) { set_error("needs mesh and materials"); return STAN_E_STATE; }
+    if (first < 0 || count <= 0 || first + count > h->n_elem || !ke) { set_error("bad element range"); return STAN_E_ARG; }
+    return element_stiffness(h, first, count, ke);
+}
+
+int stan_spmv(stan_handle *h, const double *x_full, double *y_full) {
+    STAN_TRY(check(h));
+    if (!h->assembled) { set_error("not assembled"); return STAN_E_STATE; }
+    return spmv_full(h, x_full, y_full);
+}
+
+int stan_time_spmv(stan_handle *h, int32_t reps, double *ms_per_launch, int64_t *bytes_per_launch) {
+    STAN_TRY(check(h));
+    if (!h->assembled || reps <= 0 || !ms_per_launch) { set_error("stan_time_spmv: not assembled or bad args"); return STAN_E_STATE; }
+    return time_spmv(h, reps, ms_per_launch, bytes_per_launch);
+}
+
+int stan_comm_unique_id(void *id128) { return comm_unique_id(id128); }
+
+int stan_comm_init(stan_handle *h, const void *id128) {
+    STAN_TRY(check(h));
+    return comm_init(h, id128);
+}
+
+int stan_get_partition(stan_handle *h, int64_t *first_row, int64_t *last_row) {
+    if (!h) return STAN_E_ARG;
+    if (first_row) *first_row = h->row0;
+    if (last_row) *last_row = h->row1;
+    return STAN_OK;
+}
+
+int64_t stan_kernel_launches(stan_handle *h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,512 @@
+// Jacobi-preconditioned Conjugate Gradient on the device.
+//
+// Replaces SolverFunctions.LinearSolver_CG (/root/reference/src/STAN_Solver/SolverFunctions.cs:270-330),
+// i.e. alglib.lincgsolvesparse with its defaults: x0 = 0, diagonal preconditioner applied as
+// z = r * (1/sqrt(A_ii))^2, stop on ||r||2 <= EpsF*||b||2, true-residual refresh plus energy
+// functional check every 10th iteration (terminationtype 7), MaxIts (5), breakdown (-4/-5).
+// The recurrences follow SURVEY.md Appendix A; ALGLIB's source is not in the reference checkout.
+//
+// Device design: three kernels per iteration —
+//   spmv_dot   mv = A p and p.mv       (HBM-bound: 8 B/value + 4 B per 3x3 block + vectors)
+//   update     x += a p, r -= a mv, r.r and r.(M^-1 r)
+//   direction  p = M^-1 r + b p
+// Every scalar ALGLIB computes on the host (alpha, beta, stopping tests, counters) is computed by
+// one thread of the last CTA to finish a reduction and kept in a device-resident CgState, so the
+// host enqueues whole batches of iterations and only reads the state back between batches.
+// Reductions are two-level with a fixed tree: bitwise reproducible run to run.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace stan {
+
+namespace {
+
+constexpr int VEC_THREADS = 256;
+constexpr int SPMV_THREADS = 256;
+constexpr int SPMV_WARPS = SPMV_THREADS / 32;
+
+enum ScalarStep { SC_NONE = 0, SC_INIT = 1, SC_AFTER_SPMV = 2, SC_AFTER_UPDATE = 3, SC_AFTER_REFRESH = 4 };
+
+__device__ __forceinline__ void finish_iteration(CgState *st, double cr2, double rznew) {
+    const int k = st->k + 1;
+    st->k = k;
+    st->r2 = cr2;
+    if (sqrt(cr2) <= st->epsf_bnorm) { st->type = 1; st->done = 1; return; }
+    if (st->maxits > 0 && k >= st->maxits) { st->type = 5; st->done = 1; return; }
+    const int64_t kk = k - st->counter_off;
+    double beta = 0.0;                                   // restart: p = z
+    if (kk % st->restart != 0) {
+        const double uvar = st->rz;
+        if (!isfinite(uvar) || uvar == 0.0 || !isfinite(rznew)) { st->type = -4; st->done = 1; return; }
+        beta = rznew / uvar;
+    }
+    st->beta = beta;
+    st->rz = rznew;
+}
+
+__device__ void scalar_step(CgState *st, int step) {
+    if (step == SC_INIT) {                               // partial: [0] = b.b, [1] = r.z with r = b
+        const double bn = sqrt(st->partial[0]);
+        st->bnorm = bn;
+        st->epsf_bnorm *= bn;                            // host stored EpsF here
+        st->r2 = st->partial[0];
+        st->rz = st->partial[1];
+        st->nmv = 1;                                     // r0 = b - A*x0 counted as ALGLIB does
+        if (bn == 0.0 || sqrt(st->r2) <= st->epsf_bnorm) { st->type = 1; st->done = 1; }
+        else if (!isfinite(st->r2)) { st->type = -4; st->done = 1; }
+    } else if (step == SC_AFTER_SPMV) {                  // partial[0] = p.(A p)
+        const double vmv = st->partial[0];
+        st->vmv = vmv;
+        st->nmv++;
+        if (!isfinite(vmv)) { st->type = -4; st->done = 1; }
+        else if (vmv <= 0.0) { st->type = -5; st->done = 1; }
+        else {
+            const double alpha = st->rz / vmv;
+            if (!isfinite(alpha)) { st->type = -4; st->done = 1; }
+            st->alpha = alpha;
+        }
+    } else if (step == SC_AFTER_UPDATE) {                // partial: [0] = r.r, [1] = r.z
+        finish_iteration(st, st->partial[0], st->partial[1]);
+    } else if (step == SC_AFTER_REFRESH) {               // + [2] = 2 b.cx, [3] = (A cx).cx from the SpMV
+        st->nmv++;
+        const double v1 = st->partial[3] - st->partial[2];
+        if (st->merit_check && !(v1 < st->merit)) {      // rounding stagnation: previous x is returned
+            st->k += 1;
+            st->type = 7;
+            st->done = 1;
+            return;
+        }
+        st->merit = v1;
+        st->x_in_alt ^= 1;
+        finish_iteration(st, st->partial[0], st->partial[1]);
+    }
+}
+
+__global__ void k_scalar(CgState *st, int step) {
+    if (st->done) return;
+    scalar_step(st, step);
+}
+
+// Block-level sum of NV values, published to partials[]; the last CTA to arrive folds all CTA
+// partials in a fixed order into st->partial[slot0..] and (single GPU) runs the scalar step.
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partials, unsigned int *counter, CgState *st,
+                                            int slot0, int step, bool run_scalar) {
+    __shared__ double s_red[NV][32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) s_red[i][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double x = lane < nw ? s_red[i][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) partials[(size_t)blockIdx.x * NV + i] = x;
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int ticket = atomicInc(counter, gridDim.x - 1);   // wraps to 0 for the next launch
+        s_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) acc[i] = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+#pragma unroll
+        for (int i = 0; i < NV; i++) acc[i] += __ldcg(&partials[(size_t)b * NV + i]);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double x = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) s_red[i][warp] = x;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            double x = lane < nw ? s_red[i][lane] : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) st->partial[slot0 + i] = x;
+        }
+        if (lane == 0 && run_scalar && step != SC_NONE) scalar_step(st, step);
+    }
+}
+
+// ---- SpMV -----------------------------------------------------------------------------------
+// One warp per block row.  A block row stores three scalar rows of length 3*nb back to back, so
+// lanes stream 256 B segments of each; the column of entry j is 3*bcol[j/3] + j%3, i.e. one int
+// per nine values.  x is gathered through L1/L2 (neighbouring rows share their columns).
+__device__ __forceinline__ double ld_stream(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+template <bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS)
+k_spmv(int64_t nrows, const int32_t *__restrict__ row_list, const int32_t *__restrict__ brow_ptr,
+       const int32_t *__restrict__ bcol, const double *__restrict__ vals, const double *__restrict__ x,
+       double *__restrict__ y, double *partials, unsigned int *counter, CgState *st, int slot, int step,
+       bool run_scalar) {
+    if (st && st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * SPMV_WARPS + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * SPMV_WARPS;
+    double dsum = 0.0;
+    for (int64_t it = warp0; it < nrows; it += nwarps) {
+        const int64_t row = row_list ? row_list[it] : it;
+        const int s = brow_ptr[row];
+        const int len = 3 * (brow_ptr[row + 1] - s);
+        const double *v0 = vals + 9 * (int64_t)s;
+        const double *v1 = v0 + len, *v2 = v1 + len;
+        const int32_t *cols = bcol + s;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int j0 = 0; j0 < len; j0 += 96) {
+            int jj[3];
+            double xv[3], m0[3], m1[3], m2[3];
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const int j = j0 + lane + 32 * u;
+                jj[u] = j < len ? j : len - 1;
+            }
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                m0[u] = ld_stream(v0 + jj[u]);
+                m1[u] = ld_stream(v1 + jj[u]);
+                m2[u] = ld_stream(v2 + jj[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const int blk = jj[u] / 3;
+                const int col = __ldg(cols + blk);
+                xv[u] = (j0 + lane + 32 * u < len) ? x[3 * (int64_t)col + (jj[u] - 3 * blk)] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                a0 += m0[u] * xv[u];
+                a1 += m1[u] * xv[u];
+                a2 += m2[u] * xv[u];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (lane < 3) {
+            const double yv = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+            y[3 * row + lane] = yv;
+            if (DOT) dsum += yv * x[3 * row + lane];
+        }
+    }
+    if (DOT) {
+        double v[1] = {dsum};
+        grid_reduce<1>(v, partials, counter, st, slot, step, run_scalar);
+    }
+}
+
+// ---- vector kernels --------------------------------------------------------------------------
+// init: x = 0, r = b, p = z = b d^2; sums b.b and r.z
+__global__ void __launch_bounds__(VEC_THREADS)
+k_cg_init(int64_t n, const double *__restrict__ b, const double *__restrict__ d2, double *__restrict__ x,
+          double *__restrict__ r, double *__restrict__ p, double *partials, unsigned int *counter, CgState *st,
+          bool run_scalar) {
+    double v[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double bi = b[i], z = bi * d2[i];
+        x[i] = 0.0;
+        r[i] = bi;
+        p[i] = z;
+        v[0] += bi * bi;
+        v[1] += bi * z;
+    }
+    grid_reduce<2>(v, partials, counter, st, 0, SC_INIT, run_scalar);
+}
+
+// x += alpha p; r -= alpha mv; sums r.r and r.(r d^2)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_update(int64_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
+         const double *__restrict__ mv, const double *__restrict__ d2, double *partials, unsigned int *counter,
+         CgState *st, bool run_scalar) {
+    if (st->done) return;
+    const double alpha = st->alpha;
+    double v[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] = x[i] + alpha * p[i];
+        const double ri = r[i] - alpha * mv[i];
+        r[i] = ri;
+        v[0] += ri * ri;
+        v[1] += (ri * d2[i]) * ri;
+    }
+    grid_reduce<2>(v, partials, counter, st, 0, SC_AFTER_UPDATE, run_scalar);
+}
+
+// refresh iteration, first half: cx = x + alpha p (the accepted x is left untouched)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_candidate(int64_t n, const double *__restrict__ x, const double *__restrict__ p, double *__restrict__ cx,
+            const CgState *st) {
+    if (st->done) return;
+    const double alpha = st->alpha;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        cx[i] = x[i] + alpha * p[i];
+}
+
+// refresh iteration, second half: r = b - A cx; sums r.r, r.z, 2 b.cx
+__global__ void __launch_bounds__(VEC_THREADS)
+k_refresh(int64_t n, const double *__restrict__ b, const double *__restrict__ mv, const double *__restrict__ cx,
+          const double *__restrict__ d2, double *__restrict__ r, double *partials, unsigned int *counter,
+          CgState *st, bool run_scalar) {
+    if (st->done) return;
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double ri = b[i] - mv[i];
+        r[i] = ri;
+        v[0] += ri * ri;
+        v[1] += (ri * d2[i]) * ri;
+        v[2] += 2 * b[i] * cx[i];
+    }
+    // slots 0..2 are written here; slot 3 ((A cx).cx) was produced by the SpMV before this kernel
+    grid_reduce<3>(v, partials, counter, st, 0, SC_AFTER_REFRESH, run_scalar);
+}
+
+// p = r d^2 + beta p
+__global__ void __launch_bounds__(VEC_THREADS)
+k_direction(int64_t n, const double *__restrict__ r, const double *__restrict__ d2, double *__restrict__ p,
+            const CgState *st) {
+    if (st->done) return;
+    const double beta = st->beta;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = r[i] * d2[i] + beta * p[i];
+}
+
+__global__ void k_scatter_full(int64_t nloc3, const double *__restrict__ x, double *__restrict__ ufull, int64_t dof0) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nloc3) ufull[dof0 + i] = x[i];
+}
+
+}  // namespace
+
+int64_t spmv_algorithmic_bytes(const stan_handle *h) {
+    // values 8 B each (9 per block) + one int32 column per block + per row: 2 brow_ptr reads
+    // amortised to 4 B, 3 x reads and 3 y writes of 8 B (SURVEY §8d formula for the stored format)
+    const int64_t nloc = h->row1 - h->row0;
+    return 72 * h->n_blocks + 4 * h->n_blocks + nloc * (4 + 24 + 24);
+}
+
+static int spmv_grid(const stan_handle *h, int64_t nrows) {
+    int64_t want = (nrows + SPMV_WARPS - 1) / SPMV_WARPS;
+    int64_t cap = (int64_t)h->sm_count * 8;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+static int vec_grid(const stan_handle *h, int64_t n) {
+    int64_t want = (n + VEC_THREADS * 4 - 1) / (VEC_THREADS * 4);
+    int64_t cap = (int64_t)h->sm_count * 8;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
+    cudaStream_t s = h->stream;
+    const int64_t nloc = h->row1 - h->row0, n = 3 * nloc, nx = 3 * (nloc + h->n_halo);
+    const bool multi = h->world > 1;
+    const bool single = !multi;
+    double epsf = o->epsf;
+    if (epsf == 0.0 && o->maxits == 0) epsf = 1.0e-6;      // lincgsetcond note (SolverFunctions.cs:292-293)
+    const int rupd = o->its_before_rupdate;
+    const int64_t n_global_free = 3 * h->n_nodes - h->n_fixed;
+    const int64_t restart = o->its_before_restart > 0 ? o->its_before_restart : (n_global_free > 0 ? n_global_free : 1);
+    const int off = o->zero_based_counter ? 1 : 0;
+
+    STAN_TRY(h->d_x.alloc(nx, s)); STAN_TRY(h->d_xalt.alloc(nx, s));
+    STAN_TRY(h->d_r.alloc(n, s)); STAN_TRY(h->d_p.alloc(nx, s)); STAN_TRY(h->d_mv.alloc(n, s));
+    const int gv = vec_grid(h, n), gs = spmv_grid(h, nloc);
+    const int gmax = gv > gs ? gv : gs;
+    STAN_TRY(h->d_partials.alloc((size_t)gmax * 4, s));
+    STAN_TRY(h->d_state.alloc(1, s));
+    STAN_TRY(h->d_counter.alloc(4, s));
+    STAN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, 4 * sizeof(unsigned int), s));
+    if (h->n_halo) {
+        STAN_CUDA(cudaMemsetAsync(h->d_p.p + n, 0, (nx - n) * sizeof(double), s));
+        STAN_CUDA(cudaMemsetAsync(h->d_xalt.p + n, 0, (nx - n) * sizeof(double), s));
+    }
+    CgState init;
+    memset(&init, 0, sizeof init);
+    init.epsf_bnorm = epsf;
+    init.maxits = o->maxits; init.rupdate = rupd; init.merit_check = o->merit_check; init.counter_off = off;
+    init.restart = restart;
+    CgState *hst = nullptr;
+    STAN_CUDA(cudaMallocHost((void **)&hst, sizeof(CgState)));
+    *hst = init;
+    STAN_CUDA(cudaMemcpyAsync(h->d_state.p, hst, sizeof(CgState), cudaMemcpyHostToDevice, s));
+    CgState *st = h->d_state.p;
+    double *x = h->d_x.p, *xalt = h->d_xalt.p;
+    int64_t launches = 0;
+    int spmv_launches = 0;
+    float spmv_ms = 0.f;
+    const bool timek = o->time_kernels != 0;
+    std::vector<cudaEvent_t> evs;
+
+    STAN_CUDA(cudaEventRecord(h->ev0, s));
+    auto reduce_tail = [&](int step) -> int {              // multi-GPU: all-reduce the sums, then one scalar thread
+        if (single) return STAN_OK;
+        const int cnt = step == SC_AFTER_SPMV ? 1 : (step == SC_AFTER_REFRESH ? 4 : 2);
+        STAN_TRY(comm_allreduce_sum(h, (double *)((char *)st + offsetof(CgState, partial)), cnt, s));
+        k_scalar<<<1, 1, 0, s>>>(st, step);
+        launches++;
+        return STAN_OK;
+    };
+    auto spmv = [&](double *in, int slot, int step) -> int {
+        if (multi) STAN_TRY(comm_halo_exchange(h, in, s));
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (timek) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+        k_spmv<true><<<gs, SPMV_THREADS, 0, s>>>(nloc, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in,
+                                                 h->d_mv.p, h->d_partials.p, h->d_counter.p + 2, st, slot, step, single);
+        if (timek) { cudaEventRecord(e1, s); evs.push_back(e0); evs.push_back(e1); }
+        launches++; spmv_launches++;
+        if (step != SC_NONE) STAN_TRY(reduce_tail(step));
+        return STAN_OK;
+    };
+
+    k_cg_init<<<gv, VEC_THREADS, 0, s>>>(n, h->d_b.p, h->d_d2.p, x, h->d_r.p, h->d_p.p, h->d_partials.p,
+                                         h->d_counter.p, st, single);
+    launches++;
+    STAN_TRY(reduce_tail(SC_INIT));
+
+    const int batch = rupd > 0 ? rupd : 10;
+    int k = 0;
+    bool done = false;
+    while (!done) {
+        for (int bi = 0; bi < batch; bi++) {
+            k++;
+            const int kk = k - off;
+            const bool refresh = rupd > 0 && kk % rupd == 0;
+            STAN_TRY(spmv(h->d_p.p, 0, SC_AFTER_SPMV));
+            if (!refresh) {
+                k_update<<<gv, VEC_THREADS, 0, s>>>(n, x, h->d_r.p, h->d_p.p, h->d_mv.p, h->d_d2.p, h->d_partials.p,
+                                                    h->d_counter.p, st, single);
+                launches++;
+                STAN_TRY(reduce_tail(SC_AFTER_UPDATE));
+            } else {
+                k_candidate<<<gv, VEC_THREADS, 0, s>>>(n, x, h->d_p.p, xalt, st);
+                launches++;
+                STAN_TRY(spmv(xalt, 3, SC_NONE));
+                k_refresh<<<gv, VEC_THREADS, 0, s>>>(n, h->d_b.p, h->d_mv.p, xalt, h->d_d2.p, h->d_r.p,
+                                                     h->d_partials.p, h->d_counter.p, st, single);
+                launches++;
+                STAN_TRY(reduce_tail(SC_AFTER_REFRESH));
+                double *t = x; x = xalt; xalt = t;         // accepted unless the state says type 7
+            }
+            k_direction<<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, h->d_p.p, st);
+            launches++;
+            if (o->maxits > 0 && k >= o->maxits) break;
+        }
+        STAN_CUDA(cudaMemcpyAsync(hst, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
+        STAN_CUDA(cudaStreamSynchronize(s));
+        STAN_CUDA(cudaGetLastError());
+        done = hst->done != 0;
+    }
+    STAN_CUDA(cudaEventRecord(h->ev1, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    for (size_t i = 0; i + 1 < evs.size(); i += 2) {
+        float t = 0.f;
+        // launches enqueued after the state flagged done return immediately; they are still counted
+        cudaEventElapsedTime(&t, evs[i], evs[i + 1]);
+        spmv_ms += t;
+        cudaEventDestroy(evs[i]); cudaEventDestroy(evs[i + 1]);
+    }
+    // accepted iterate: d_x unless an odd number of refreshes were accepted
+    h->x_in_alt = hst->x_in_alt != 0;
+    rep->terminationtype = hst->type;
+    rep->iterationscount = hst->k;
+    rep->nmv = hst->nmv;
+    rep->spmv_launches = spmv_launches;
+    rep->r2 = hst->r2;
+    rep->bnorm = hst->bnorm;
+    rep->solve_ms = ms;
+    rep->spmv_ms = spmv_ms;
+    rep->spmv_bytes = spmv_algorithmic_bytes(h);
+    rep->iter_bytes = rep->spmv_bytes + 88 * n;
+    rep->kernel_launches = launches;
+    h->launches += launches;
+    cudaFreeHost(hst);
+    h->solved = true;
+    return STAN_OK;
+}
+
+int spmv_full(stan_handle *h, const double *x_full, double *y_full) {
+    if (h->world != 1) { set_error("stan_spmv is single-GPU only"); return STAN_E_STATE; }
+    cudaStream_t s = h->stream;
+    const int64_t n = 3 * h->n_nodes;
+    DevBuf<double> x, y;
+    STAN_TRY(x.alloc(n, s)); STAN_TRY(y.alloc(n, s));
+    STAN_CUDA(cudaMemcpyAsync(x.p, x_full, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    k_spmv<false><<<spmv_grid(h, h->n_nodes), SPMV_THREADS, 0, s>>>(h->n_nodes, nullptr, h->d_brow_ptr.p,
+                                                                     h->bcol_x, h->d_vals.p, x.p, y.p, nullptr,
+                                                                     nullptr, nullptr, 0, SC_NONE, false);
+    STAN_CUDA(cudaGetLastError());
+    STAN_CUDA(cudaMemcpyAsync(y_full, y.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    x.release(s); y.release(s);
+    h->launches += 1;
+    return STAN_OK;
+}
+
+int time_spmv(stan_handle *h, int reps, double *ms_out, int64_t *bytes) {
+    cudaStream_t s = h->stream;
+    const int64_t nloc = h->row1 - h->row0, nx = 3 * (nloc + h->n_halo);
+    DevBuf<double> x, y;
+    STAN_TRY(x.alloc(nx, s)); STAN_TRY(y.alloc(3 * nloc, s));
+    STAN_CUDA(cudaMemsetAsync(x.p, 0, nx * sizeof(double), s));
+    const int gs = spmv_grid(h, nloc);
+    for (int w = 0; w < 3; w++)
+        k_spmv<false><<<gs, SPMV_THREADS, 0, s>>>(nloc, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, x.p, y.p,
+                                                  nullptr, nullptr, nullptr, 0, SC_NONE, false);
+    STAN_CUDA(cudaEventRecord(h->ev2, s));
+    for (int r = 0; r < reps; r++)
+        k_spmv<false><<<gs, SPMV_THREADS, 0, s>>>(nloc, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, x.p, y.p,
+                                                  nullptr, nullptr, nullptr, 0, SC_NONE, false);
+    STAN_CUDA(cudaEventRecord(h->ev3, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    STAN_CUDA(cudaGetLastError());
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev2, h->ev3);
+    *ms_out = ms / reps;
+    if (bytes) *bytes = spmv_algorithmic_bytes(h);
+    x.release(s); y.release(s);
+    h->launches += reps + 3;
+    return STAN_OK;
+}
+
+int scatter_solution(stan_handle *h) {
+    cudaStream_t s = h->stream;
+    const int64_t nloc = h->row1 - h->row0;
+    STAN_TRY(h->d_ufull.alloc(3 * h->n_nodes, s));
+    const double *x = h->x_in_alt ? h->d_xalt.p : h->d_x.p;
+    if (h->world == 1) {
+        STAN_CUDA(cudaMemcpyAsync(h->d_ufull.p, x, 3 * nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    } else {
+        STAN_TRY(comm_allgather_rows(h, x, h->d_ufull.p, s));
+    }
+    return STAN_OK;
+}
+
+}  // namespace stan

@@ -1,0 +1,260 @@
+// Multi-GPU plumbing: one process per GPU, contiguous BFS-node row ranges.
+//
+// The reference is single-process (its only parallelism is Parallel.ForEach,
+// /root/reference/src/STAN_Solver/SolverFunctions.cs:129); this layer is new.  NCCL is resolved at
+// run time with dlopen so the single-GPU library has no NCCL dependency and a process that already
+// loaded torch's libnccl.so.2 shares that copy.  Per SpMV each rank sends the entries of p that
+// its neighbours' boundary rows reference and receives its own halo; CG dot products are one
+// small all-reduce each.  Because adjacency is symmetric, a rank derives both its halo list and
+// its send lists from its own block columns — no set-up communication is needed.
+#include <cub/device/device_scan.cuh>
+#include <dlfcn.h>
+
+#include "common.cuh"
+
+namespace stan {
+
+typedef struct { char internal[128]; } nccl_uid;
+typedef void *nccl_comm;
+
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(nccl_uid *) = nullptr;
+    int (*CommInitRank)(nccl_comm *, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+
+static NcclApi g_nccl;
+constexpr int NCCL_F64 = 8, NCCL_SUM = 0;
+
+static int load_nccl() {
+    if (g_nccl.lib) return STAN_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    void *lib = nullptr;
+    for (int i = 0; names[i] && !lib; i++) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) {
+        const char *env = getenv("STAN_NCCL_LIB");
+        if (env) lib = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!lib) { set_error("cannot dlopen libnccl.so.2 (set STAN_NCCL_LIB): %s", dlerror()); return STAN_E_COMM; }
+#define SYM(field, name)                                                              \
+    *(void **)(&g_nccl.field) = dlsym(lib, name);                                     \
+    if (!g_nccl.field) { set_error("libnccl lacks %s", name); return STAN_E_COMM; }
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.lib = lib;
+    return STAN_OK;
+}
+
+#define STAN_NCCL(call)                                                                            \
+    do {                                                                                           \
+        int r__ = (call);                                                                          \
+        if (r__ != 0) { set_error("%s -> %s", #call, g_nccl.GetErrorString(r__)); return STAN_E_COMM; } \
+    } while (0)
+
+struct Comm {
+    nccl_comm comm = nullptr;
+    std::vector<int64_t> bound;            // world+1 row bounds
+    std::vector<int64_t> recv_off, recv_cnt;   // per peer: segment of the halo region (nodes)
+    std::vector<int64_t> send_off, send_cnt;   // per peer: segment of the send list (nodes)
+    DevBuf<int32_t> d_send_rows;           // local row index of every node to send, grouped by peer
+    DevBuf<double> d_sendbuf;              // 3 doubles per send node
+    DevBuf<double> d_gather;               // padded all-gather staging
+    int64_t n_send = 0, max_rows = 0;
+};
+
+int comm_unique_id(void *id128) {
+    STAN_TRY(load_nccl());
+    STAN_NCCL(g_nccl.GetUniqueId((nccl_uid *)id128));
+    return STAN_OK;
+}
+
+int comm_init(stan_handle *h, const void *id128) {
+    if (h->world <= 1) return STAN_OK;
+    STAN_TRY(load_nccl());
+    if (!h->comm) h->comm = new Comm();
+    nccl_uid id;
+    memcpy(&id, id128, sizeof id);
+    STAN_CUDA(cudaSetDevice(h->device));
+    STAN_NCCL(g_nccl.CommInitRank(&h->comm->comm, h->world, id, h->rank));
+    return STAN_OK;
+}
+
+void comm_destroy(stan_handle *h) {
+    if (!h->comm) return;
+    if (h->comm->comm) g_nccl.CommDestroy(h->comm->comm);
+    h->comm->d_send_rows.release(h->stream);
+    h->comm->d_sendbuf.release(h->stream);
+    h->comm->d_gather.release(h->stream);
+    delete h->comm;
+    h->comm = nullptr;
+}
+
+int comm_allreduce_sum(stan_handle *h, double *d_buf, int count, cudaStream_t s) {
+    if (h->world <= 1) return STAN_OK;
+    STAN_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)count, NCCL_F64, NCCL_SUM, h->comm->comm, s));
+    return STAN_OK;
+}
+
+namespace {
+
+__global__ void k_mark_halo(int64_t nblk, const int32_t *__restrict__ bcol, int64_t row0, int64_t row1,
+                            int32_t *__restrict__ flag) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nblk) return;
+    int32_t q = bcol[t];
+    if (q < row0 || q >= row1) flag[q] = 1;
+}
+
+__global__ void k_localize_cols(int64_t nblk, const int32_t *__restrict__ bcol, int64_t row0, int64_t row1,
+                                const int32_t *__restrict__ slot, int32_t *__restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nblk) return;
+    int32_t q = bcol[t];
+    out[t] = (q >= row0 && q < row1) ? (int32_t)(q - row0) : (int32_t)(row1 - row0) + slot[q];
+}
+
+// bit s of mask[row] is set when the row has a column owned by rank s
+__global__ void k_peer_mask(int64_t nloc, const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
+                            int world, const int64_t *__restrict__ bound, int64_t row0, int64_t row1,
+                            uint32_t *__restrict__ mask) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nloc) return;
+    uint32_t m = 0;
+    for (int s = brow_ptr[p]; s < brow_ptr[p + 1]; s++) {
+        int64_t q = bcol[s];
+        if (q >= row0 && q < row1) continue;
+        int r = 0;
+        while (r + 1 < world && q >= bound[r + 1]) r++;
+        m |= 1u << r;
+    }
+    mask[p] = m;
+}
+
+__global__ void k_pack(int64_t n_send, const int32_t *__restrict__ rows, const double *__restrict__ vec,
+                       double *__restrict__ buf) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * n_send) return;
+    buf[t] = vec[3 * (int64_t)rows[t / 3] + t % 3];
+}
+
+}  // namespace
+
+void partition_rows(stan_handle *h) {
+    h->row0 = h->n_nodes * (int64_t)h->rank / h->world;
+    h->row1 = h->n_nodes * (int64_t)(h->rank + 1) / h->world;
+}
+
+int comm_build_halo(stan_handle *h) {
+    cudaStream_t s = h->stream;
+    const int64_t nloc = h->row1 - h->row0, nn = h->n_nodes;
+    h->n_halo = 0;
+    if (h->world <= 1) { h->bcol_x = h->d_bcol.p; return STAN_OK; }
+    if (!h->comm || !h->comm->comm) { set_error("world > 1 but stan_comm_init was not called"); return STAN_E_STATE; }
+    Comm *c = h->comm;
+    const int W = h->world;
+    c->bound.resize(W + 1);
+    for (int r = 0; r <= W; r++) c->bound[r] = nn * (int64_t)r / W;
+    c->max_rows = 0;
+    for (int r = 0; r < W; r++) c->max_rows = std::max(c->max_rows, c->bound[r + 1] - c->bound[r]);
+
+    DevBuf<int32_t> flag, slot;
+    STAN_TRY(flag.alloc(nn + 1, s)); STAN_TRY(slot.alloc(nn + 1, s));
+    STAN_CUDA(cudaMemsetAsync(flag.p, 0, (nn + 1) * sizeof(int32_t), s));
+    k_mark_halo<<<div_up(h->n_blocks, 256), 256, 0, s>>>(h->n_blocks, h->d_bcol.p, h->row0, h->row1, flag.p);
+    {
+        size_t bytes = 0;
+        STAN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.p, slot.p, nn + 1, s));
+        void *tmp = nullptr;
+        STAN_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 1, s));
+        cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, bytes, flag.p, slot.p, nn + 1, s);
+        cudaFreeAsync(tmp, s);
+        STAN_CUDA(e);
+    }
+    STAN_TRY(h->d_bcol_loc.alloc(h->n_blocks, s));
+    k_localize_cols<<<div_up(h->n_blocks, 256), 256, 0, s>>>(h->n_blocks, h->d_bcol.p, h->row0, h->row1, slot.p,
+                                                             h->d_bcol_loc.p);
+    h->bcol_x = h->d_bcol_loc.p;
+    // halo segment of every owner = difference of the scan at its bounds
+    std::vector<int32_t> at(W + 1);
+    for (int r = 0; r <= W; r++)
+        STAN_CUDA(cudaMemcpyAsync(&at[r], slot.p + c->bound[r], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    // send lists from the peer mask of the owned rows
+    DevBuf<uint32_t> mask; DevBuf<int64_t> dbound;
+    STAN_TRY(mask.alloc(nloc, s)); STAN_TRY(dbound.alloc(W + 1, s));
+    STAN_CUDA(cudaMemcpyAsync(dbound.p, c->bound.data(), (W + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    k_peer_mask<<<div_up(nloc, 256), 256, 0, s>>>(nloc, h->d_brow_ptr.p, h->d_bcol.p, W, dbound.p, h->row0, h->row1,
+                                                  mask.p);
+    std::vector<uint32_t> hmask((size_t)nloc);
+    STAN_CUDA(cudaMemcpyAsync(hmask.data(), mask.p, nloc * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    STAN_CUDA(cudaGetLastError());
+    flag.release(s); slot.release(s); mask.release(s); dbound.release(s);
+
+    c->recv_off.assign(W, 0); c->recv_cnt.assign(W, 0); c->send_off.assign(W, 0); c->send_cnt.assign(W, 0);
+    for (int r = 0; r < W; r++) { c->recv_off[r] = at[r]; c->recv_cnt[r] = at[r + 1] - at[r]; }
+    h->n_halo = at[W];
+    std::vector<int32_t> rows;
+    for (int r = 0; r < W; r++) {
+        c->send_off[r] = (int64_t)rows.size();
+        if (r != h->rank)
+            for (int64_t p = 0; p < nloc; p++)
+                if (hmask[p] & (1u << r)) rows.push_back((int32_t)p);
+        c->send_cnt[r] = (int64_t)rows.size() - c->send_off[r];
+    }
+    c->n_send = (int64_t)rows.size();
+    STAN_TRY(c->d_send_rows.alloc(rows.size(), s));
+    STAN_TRY(c->d_sendbuf.alloc(3 * rows.size(), s));
+    if (!rows.empty())
+        STAN_CUDA(cudaMemcpyAsync(c->d_send_rows.p, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    h->launches += 4;
+    return STAN_OK;
+}
+
+// vec holds 3*nloc owned entries followed by 3*n_halo halo entries
+int comm_halo_exchange(stan_handle *h, double *d_vec, cudaStream_t s) {
+    if (h->world <= 1) return STAN_OK;
+    Comm *c = h->comm;
+    const int64_t nloc = h->row1 - h->row0;
+    if (c->n_send) {
+        k_pack<<<div_up(3 * c->n_send, 256), 256, 0, s>>>(c->n_send, c->d_send_rows.p, d_vec, c->d_sendbuf.p);
+        h->launches += 1;
+    }
+    STAN_NCCL(g_nccl.GroupStart());
+    for (int r = 0; r < h->world; r++) {
+        if (r == h->rank) continue;
+        if (c->send_cnt[r])
+            STAN_NCCL(g_nccl.Send(c->d_sendbuf.p + 3 * c->send_off[r], (size_t)(3 * c->send_cnt[r]), NCCL_F64, r, c->comm, s));
+        if (c->recv_cnt[r])
+            STAN_NCCL(g_nccl.Recv(d_vec + 3 * (nloc + c->recv_off[r]), (size_t)(3 * c->recv_cnt[r]), NCCL_F64, r, c->comm, s));
+    }
+    STAN_NCCL(g_nccl.GroupEnd());
+    return STAN_OK;
+}
+
+// every rank ends with the full DOF-ordered vector (rows are contiguous per rank)
+int comm_allgather_rows(stan_handle *h, const double *d_local, double *d_full, cudaStream_t s) {
+    Comm *c = h->comm;
+    const int W = h->world;
+    const int64_t nloc = h->row1 - h->row0;
+    STAN_TRY(c->d_gather.alloc((size_t)(3 * c->max_rows) * (W + 1), s));
+    double *stage = c->d_gather.p, *all = c->d_gather.p + 3 * c->max_rows;
+    STAN_CUDA(cudaMemcpyAsync(stage, d_local, 3 * nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    STAN_NCCL(g_nccl.AllGather(stage, all, (size_t)(3 * c->max_rows), NCCL_F64, c->comm, s));
+    for (int r = 0; r < W; r++)
+        STAN_CUDA(cudaMemcpyAsync(d_full + 3 * c->bound[r], all + (size_t)r * 3 * c->max_rows,
+                                  3 * (c->bound[r + 1] - c->bound[r]) * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    return STAN_OK;
+}
+
+}  // namespace stan

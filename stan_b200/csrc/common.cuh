@@ -1,0 +1,185 @@
+// Shared declarations of libstan_b200 (sm_100a).  See include/stan_b200.h for the ABI and
+// DESIGN.md for the data layout.  Nothing here depends on PyTorch.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/stan_b200.h"
+
+namespace stan {
+
+void set_error(const char *fmt, ...);
+
+#define STAN_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            stan::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));    \
+            return STAN_E_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+#define STAN_TRY(call)                   \
+    do {                                 \
+        int rc__ = (call);               \
+        if (rc__ != STAN_OK) return rc__; \
+    } while (0)
+
+// Device buffer owned by the handle; stream-ordered allocation from the device's default pool so
+// repeated assemble/solve cycles reuse memory instead of paying cudaMalloc every step.
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count, cudaStream_t s) {
+        if (count <= n && p) return STAN_OK;
+        release(s);
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMallocAsync((void **)&p, count * sizeof(T), s);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            n = 0;
+            set_error("cudaMallocAsync(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+            return STAN_E_CUDA;
+        }
+        n = count;
+        return STAN_OK;
+    }
+    void release(cudaStream_t s) {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+// Device-resident CG scalars: every decision ALGLIB's lincgiteration takes on the host is taken
+// here by one thread, so a batch of iterations can be enqueued without a host round trip.
+struct CgState {
+    double bnorm, epsf_bnorm;
+    double rz;        // r.z of the current residual
+    double vmv;       // p.(A p)
+    double alpha, beta;
+    double r2;        // ||r||^2 of the accepted iterate
+    double merit;     // best x'Ax - 2b'x so far
+    double partial[4];// all-reduced partial sums of the running phase
+    int32_t k;        // completed iterations
+    int32_t done;     // 0 = running
+    int32_t type;     // terminationtype once done
+    int32_t nmv;
+    int32_t maxits, rupdate, merit_check, counter_off;
+    int64_t restart;
+    int32_t x_in_alt; // 1 when the accepted iterate lives in the alternate x buffer
+    int32_t pad;
+};
+
+struct Comm;  // comm.cu
+
+}  // namespace stan
+
+struct stan_handle {
+    int device = 0;
+    int rank = 0, world = 1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+
+    // ---- model (global, every rank holds the whole mesh) ----
+    int64_t n_nodes = 0, n_elem = 0;
+    int32_t n_mat = 0;
+    bool have_mesh = false, have_mat = false, have_dof = false, assembled = false, solved = false,
+         recovered = false;
+    std::vector<int32_t> h_conn;        // kept for the native AssignDOF only
+    std::vector<int32_t> h_node_index;  // host copy of the dof map (RHS assembly, partitioning)
+    stan::DevBuf<double> d_xyz;         // 3*n_nodes
+    stan::DevBuf<int32_t> d_conn;       // 8*n_elem
+    stan::DevBuf<uint8_t> d_etype;      // n_elem
+    stan::DevBuf<int32_t> d_emat;       // n_elem
+    stan::DevBuf<double> d_lambda, d_G; // n_mat (Material.cs:39-40)
+    stan::DevBuf<int32_t> d_node_index; // n_nodes: BFS index of node (DOF/3)
+    stan::DevBuf<int32_t> d_inv;        // n_nodes: node at BFS index
+    std::vector<int32_t> h_spc_node;
+    std::vector<double> h_spc_val;
+    std::vector<int32_t> h_load_node;
+    std::vector<double> h_load_val;
+
+    // ---- partition ----
+    int64_t row0 = 0, row1 = 0;         // owned BFS rows [row0, row1)
+    int64_t n_halo = 0;                 // halo nodes appended after the owned rows in x vectors
+
+    // ---- assembled system (local rows) ----
+    stan::DevBuf<int32_t> d_inc_ptr;    // nloc+1: incidence CSR (row -> (elem<<3 | local node))
+    stan::DevBuf<int32_t> d_inc;        //
+    stan::DevBuf<int32_t> d_brow_ptr;   // nloc+1: block-row pointers
+    stan::DevBuf<int32_t> d_bcol;       // global BFS column node of every block
+    stan::DevBuf<int32_t> d_bcol_loc;   // local x index of every block (owned: q-row0, halo: nloc+slot)
+    const int32_t *bcol_x = nullptr;    // what SpMV indexes x with: d_bcol (1 GPU) or d_bcol_loc
+    stan::DevBuf<double> d_vals;        // 9 per block; per block row: 3 scalar rows of length 3*nb
+    stan::DevBuf<uint8_t> d_fixed;      // 3*n_nodes (global): 1 = SPC-fixed DOF
+    stan::DevBuf<int32_t> d_red;        // 3*n_nodes: nDOF_reduction (Solver.cs:121-132)
+    stan::DevBuf<double> d_b;           // 3*nloc RHS in full DOF space (0 at fixed)
+    stan::DevBuf<double> d_d2;          // 3*nloc: (1/sqrt(A_ii))^2
+    stan::DevBuf<int32_t> d_err;        // device error flags
+    int64_t n_blocks = 0, n_fixed = 0, nnz_upper = 0;
+    int32_t max_group_blocks = 0;       // max blocks in a 32-row group (assembly smem sizing)
+
+    // ---- CG work vectors (3*(nloc+n_halo) where halo is needed) ----
+    stan::DevBuf<double> d_x, d_xalt, d_r, d_p, d_mv, d_partials;
+    stan::DevBuf<stan::CgState> d_state;
+    stan::DevBuf<unsigned int> d_counter;
+    bool x_in_alt = false;
+
+    // ---- results ----
+    stan::DevBuf<double> d_ufull;       // 3*n_nodes in DOF order (all ranks after the gather)
+    stan::DevBuf<double> d_strain, d_stress;  // 48*n_elem
+
+    stan::Comm *comm = nullptr;
+    int64_t launches = 0;
+};
+
+namespace stan {
+
+// dofmap.cpp
+int assign_dof_host(int64_t n_nodes, int64_t n_elem, const int32_t *conn, int32_t *node_index);
+
+// pattern.cu
+int build_system_pattern(stan_handle *h);
+int build_rhs(stan_handle *h);
+int export_csr_upper_size(stan_handle *h, int64_t *n, int64_t *nnz);
+int export_csr_upper(stan_handle *h, int64_t *rowptr, int32_t *col, double *val);
+
+// assembly.cu
+int upload_fe_tables();
+void host_fe_tables(double *tab /*9*24*/);
+int run_assembly(stan_handle *h);
+int element_stiffness(stan_handle *h, int64_t first, int64_t count, double *ke_host);
+
+// cg.cu
+int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep);
+int spmv_full(stan_handle *h, const double *x_full, double *y_full);
+int time_spmv(stan_handle *h, int reps, double *ms, int64_t *bytes);
+int64_t spmv_algorithmic_bytes(const stan_handle *h);
+int scatter_solution(stan_handle *h);
+
+// recovery.cu
+int run_recovery(stan_handle *h, stan_recovery_stats *st);
+
+// comm.cu
+int comm_unique_id(void *id128);
+int comm_init(stan_handle *h, const void *id128);
+void comm_destroy(stan_handle *h);
+int comm_allreduce_sum(stan_handle *h, double *d_buf, int count, cudaStream_t s);
+int comm_halo_exchange(stan_handle *h, double *d_vec, cudaStream_t s);
+int comm_allgather_rows(stan_handle *h, const double *d_local, double *d_full, cudaStream_t s);
+int comm_build_halo(stan_handle *h);
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace stan

@@ -1,0 +1,176 @@
+// Gauss-point strain/stress recovery and extrapolation to the element nodes.
+//
+// Replaces Element.Recovery_Stress + Update_StrainStress
+// (/root/reference/src/STAN_Database/Element.cs:211-246, 257-267) and the dU_buffer hand-off of
+// /root/reference/src/STAN_Solver/Solver.cs:168-178.  The reference keeps BL[g] (6x24) and J[g]
+// cached on every element from K_Initial (~9.8 KB per element); here they are recomputed from the
+// 8 node coordinates, so nothing but the mesh and U is read and only the 2 x 48 results are written.
+//
+// One thread per (element, Gauss point) computes eps_g = BL[g] dU and sig_g = D eps_g; the 8
+// threads of an element exchange them through shared memory and thread i forms the nodal values
+// sum_g N[i][g] * value_g (FE_Library.cs:105-116).  HEX8_G1 has one Gauss point whose value every
+// node receives (the reference indexes N[i][g] out of range there and throws).
+#include "common.cuh"
+
+namespace stan {
+
+namespace {
+
+__constant__ double c_rdNl[9][24];   // same table as assembly.cu (per-TU constant copy)
+__constant__ double c_N[8][8];       // N[i][g], HEX8_ShapeFunctions(node i, 1/sqrt(3)) FE_Library.cs:285-321
+
+constexpr int REC_THREADS = 128;     // 16 elements per CTA
+
+__global__ void __launch_bounds__(REC_THREADS)
+k_recover(int64_t n_elem, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
+          const int32_t *__restrict__ node_index, const uint8_t *__restrict__ etype, const int32_t *__restrict__ emat,
+          const double *__restrict__ lam_tab, const double *__restrict__ G_tab, const double *__restrict__ ufull,
+          double *__restrict__ strain, double *__restrict__ stress, int32_t *err) {
+    __shared__ double s_val[REC_THREADS / 8][8][12];
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t e = t >> 3;
+    const int g = (int)(t & 7), le = threadIdx.x >> 3;
+    const bool valid = e < n_elem;
+    int type = STAN_HEX8_G2;
+    if (valid) {
+        type = etype[e];
+        double val[12];
+#pragma unroll
+        for (int c = 0; c < 12; c++) val[c] = 0.0;
+        if (type == STAN_HEX8_G2 || g == 0) {
+            const int gp = (type == STAN_HEX8_G2) ? g : 8;
+            const int4 c0 = *reinterpret_cast<const int4 *>(conn + 8 * e);
+            const int4 c1 = *reinterpret_cast<const int4 *>(conn + 8 * e + 4);
+            const int nd[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            double X[24], U[24];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const double *p = xyz + 3 * (int64_t)nd[k];
+                const double *u = ufull + 3 * (int64_t)node_index[nd[k]];   // Element.cs:214-221
+                X[3 * k] = p[0]; X[3 * k + 1] = p[1]; X[3 * k + 2] = p[2];
+                U[3 * k] = u[0]; U[3 * k + 1] = u[1]; U[3 * k + 2] = u[2];
+            }
+            double J[9];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) s += c_rdNl[gp][r * 8 + k] * X[k * 3 + c];
+                    J[r * 3 + c] = s;
+                }
+            const double det = J[0] * J[4] * J[8] + J[3] * J[7] * J[2] + J[6] * J[1] * J[5] - J[2] * J[4] * J[6] -
+                               J[0] * J[5] * J[7] - J[8] * J[1] * J[3];
+            if (det == 0.0) atomicOr(err + 2, 1);
+            const double inv = 1.0 / det;
+            double Ji[9];
+            Ji[0] = inv * (J[4] * J[8] - J[5] * J[7]);
+            Ji[1] = inv * (J[2] * J[7] - J[1] * J[8]);
+            Ji[2] = inv * (J[1] * J[5] - J[2] * J[4]);
+            Ji[3] = inv * (J[5] * J[6] - J[3] * J[8]);
+            Ji[4] = inv * (J[0] * J[8] - J[2] * J[6]);
+            Ji[5] = inv * (J[2] * J[3] - J[0] * J[5]);
+            Ji[6] = inv * (J[3] * J[7] - J[4] * J[6]);
+            Ji[7] = inv * (J[1] * J[6] - J[0] * J[7]);
+            Ji[8] = inv * (J[0] * J[4] - J[1] * J[3]);
+            // eps = BL0 dU in node order (BL0_Matrix, Element.cs:316-324; MultiplyVector j ascending)
+            double ex = 0, ey = 0, ez = 0, exy = 0, eyz = 0, exz = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const double dx = Ji[0] * c_rdNl[gp][k] + Ji[1] * c_rdNl[gp][8 + k] + Ji[2] * c_rdNl[gp][16 + k];
+                const double dy = Ji[3] * c_rdNl[gp][k] + Ji[4] * c_rdNl[gp][8 + k] + Ji[5] * c_rdNl[gp][16 + k];
+                const double dz = Ji[6] * c_rdNl[gp][k] + Ji[7] * c_rdNl[gp][8 + k] + Ji[8] * c_rdNl[gp][16 + k];
+                const double ux = U[3 * k], uy = U[3 * k + 1], uz = U[3 * k + 2];
+                ex += dx * ux; ey += dy * uy; ez += dz * uz;
+                exy += dy * ux; exy += dx * uy;
+                eyz += dz * uy; eyz += dy * uz;
+                exz += dz * ux; exz += dx * uz;
+            }
+            const int mat = emat[e];
+            const double lam = lam_tab[mat], G = G_tab[mat], d0 = lam + (2 * G);
+            val[0] = ex; val[1] = ey; val[2] = ez; val[3] = exy; val[4] = eyz; val[5] = exz;
+            val[6] = d0 * ex + lam * ey + lam * ez;      // D.MultiplyVector, Material.cs:42-53
+            val[7] = lam * ex + d0 * ey + lam * ez;
+            val[8] = lam * ex + lam * ey + d0 * ez;
+            val[9] = G * exy; val[10] = G * eyz; val[11] = G * exz;
+        }
+#pragma unroll
+        for (int c = 0; c < 12; c++) s_val[le][g][c] = val[c];
+    }
+    __syncthreads();
+    if (!valid) return;
+    const int i = g;                                     // this thread now owns element node i
+    double out[12];
+#pragma unroll
+    for (int c = 0; c < 12; c++) out[c] = 0.0;
+    if (type == STAN_HEX8_G2) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {                    // Element.cs:238-245, g ascending
+            const double w = c_N[i][q];
+#pragma unroll
+            for (int c = 0; c < 12; c++) out[c] += s_val[le][q][c] * w;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 12; c++) out[c] = s_val[le][0][c];
+    }
+    double *so = strain + e * 48 + i * 6, *to = stress + e * 48 + i * 6;   // Update_StrainStress :257-267
+#pragma unroll
+    for (int c = 0; c < 6; c += 2) {
+        *reinterpret_cast<double2 *>(so + c) = make_double2(out[c], out[c + 1]);
+        *reinterpret_cast<double2 *>(to + c) = make_double2(out[6 + c], out[6 + c + 1]);
+    }
+}
+
+bool g_tables_ready = false;
+
+}  // namespace
+
+static int upload_recovery_tables() {
+    double tab[9 * 24];
+    host_fe_tables(tab);
+    STAN_CUDA(cudaMemcpyToSymbol(c_rdNl, tab, sizeof tab));
+    static const double S[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1},
+                                   {-1, -1, 1},  {1, -1, 1},  {1, 1, 1},  {-1, 1, 1}};
+    const double gl = sqrt(1.0 / 3.0);
+    double N[64];
+    for (int i = 0; i < 8; i++) {
+        const double xi = S[i][0] / gl, eta = S[i][1] / gl, zeta = S[i][2] / gl;
+        for (int k = 0; k < 8; k++)
+            N[i * 8 + k] = 1.0 / 8.0 * (1 + S[k][0] * xi) * (1 + S[k][1] * eta) * (1 + S[k][2] * zeta);
+    }
+    STAN_CUDA(cudaMemcpyToSymbol(c_N, N, sizeof N));
+    return STAN_OK;
+}
+
+int run_recovery(stan_handle *h, stan_recovery_stats *stats) {
+    cudaStream_t s = h->stream;
+    STAN_TRY(upload_recovery_tables());
+    STAN_TRY(scatter_solution(h));
+    STAN_TRY(h->d_strain.alloc((size_t)48 * h->n_elem, s));
+    STAN_TRY(h->d_stress.alloc((size_t)48 * h->n_elem, s));
+    STAN_CUDA(cudaMemsetAsync(h->d_err.p, 0, 4 * sizeof(int32_t), s));
+    STAN_CUDA(cudaEventRecord(h->ev0, s));
+    k_recover<<<div_up(8 * h->n_elem, REC_THREADS), REC_THREADS, 0, s>>>(
+        h->n_elem, h->d_conn.p, h->d_xyz.p, h->d_node_index.p, h->d_etype.p, h->d_emat.p, h->d_lambda.p, h->d_G.p,
+        h->d_ufull.p, h->d_strain.p, h->d_stress.p, h->d_err.p);
+    STAN_CUDA(cudaGetLastError());
+    STAN_CUDA(cudaEventRecord(h->ev1, s));
+    int32_t herr[4];
+    STAN_CUDA(cudaMemcpyAsync(herr, h->d_err.p, sizeof herr, cudaMemcpyDeviceToHost, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    if (herr[2]) { set_error("singular Jacobian (det == 0) during recovery"); return STAN_E_SINGULAR; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->launches += 1;
+    if (stats) {
+        stats->recover_ms = ms;
+        stats->recover_bytes = h->n_elem * (32 + 768) + 24 * h->n_nodes * 2;
+        stats->kernel_launches = 1;
+    }
+    h->recovered = true;
+    return STAN_OK;
+}
+
+}  // namespace stan

@@ -1,0 +1,251 @@
+"""GPU parity: libstan_b200.so (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): DOF numbering and CSR pattern bit-exact; displacements within
+1e-10 relative and stresses within 1e-8 relative at an identical CG tolerance.
+"""
+import numpy as np
+import pytest
+
+from stan_b200 import mesh, native
+from stan_b200.solver import Solver
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def solver():
+    s = Solver()
+    yield s
+    s.close()
+
+
+def _shuffled(m, seed=0):
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(m.n_elem)
+    m.conn = np.ascontiguousarray(m.conn[perm]); m.elem_type = m.elem_type[perm]
+    m.elem_mat = m.elem_mat[perm]; m.elem_pid = m.elem_pid[perm]
+    return m
+
+
+@pytest.mark.parametrize("dims", [(2, 2, 2), (3, 4, 9), (1, 1, 7), (6, 5, 4)])
+def test_assign_dof_bit_exact(solver, oracle, dims):
+    for m in (mesh.beam(*dims), _shuffled(mesh.beam(*dims), 3)):
+        solver.SetModel(m)
+        assert np.array_equal(solver.AssignDOF(), oracle.assign_dof(m))   # Database.cs:140-234
+
+
+def test_assign_dof_errors(solver):
+    a, b = mesh.beam(1, 1, 1), mesh.beam(1, 1, 1)
+    a.xyz = np.vstack([a.xyz, b.xyz + 5.0]); a.conn = np.vstack([a.conn, b.conn + 8]).astype(np.int32)
+    a.elem_type = np.repeat(a.elem_type, 2); a.elem_mat = np.repeat(a.elem_mat, 2)
+    solver.SetModel(a)
+    with pytest.raises(native.StanError) as ei:
+        solver.AssignDOF()
+    assert ei.value.code == native.E_DOFMAP
+
+
+@pytest.mark.parametrize("etype", [mesh.HEX8_G2, mesh.HEX8_G1])
+def test_element_stiffness(solver, oracle, etype):
+    m = mesh.beam(4, 3, 5, jitter=True, elem_type=etype, n_parts=2)
+    solver.SetModel(m)
+    ke = solver.K_Initial()                                              # Element.cs:118-155
+    for e in range(m.n_elem):
+        D = oracle.elastic_D(m.mat_E[m.elem_mat[e]], m.mat_nu[m.elem_mat[e]])
+        ref = oracle.k_initial(etype, m.xyz[m.conn[e]], D)
+        assert np.abs(ke[e] - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def _assembled(solver, oracle, m):
+    solver.SetModel(m)
+    ni = solver.AssignDOF()
+    solver.ParallelAssembly_K()
+    red, nfix = oracle.spc_reduction(m, ni)
+    return ni, red, oracle.assemble_upper(m, ni, red)
+
+
+def _cases():
+    a = mesh.beam(4, 4, 6, jitter=True)
+    b = _shuffled(mesh.beam(3, 5, 4, jitter=True, n_parts=2), 7)
+    c = mesh.beam(3, 3, 5, jitter=True)                                   # partial SPC: breaks 3x3 blocks
+    c.spc_val[::2, 1] = 0.0; c.spc_val[1::3, 2] = 0.0
+    c.spc_node = np.concatenate([c.spc_node, [40, 41]]).astype(np.int32)
+    c.spc_val = np.vstack([c.spc_val, [[0, 1, 0], [1, 0, 0]]])
+    d = mesh.beam(3, 3, 4, jitter=True, elem_type=mesh.HEX8_G1)
+    return {"plain": a, "shuffled_2mat": b, "partial_spc": c, "g1": d}
+
+
+@pytest.mark.parametrize("name", ["plain", "shuffled_2mat", "partial_spc", "g1"])
+def test_csr_pattern_bit_exact_values_close(solver, oracle, name):
+    m = _cases()[name]
+    ni, red, K = _assembled(solver, oracle, m)
+    assert np.array_equal(solver.nDOF_reduction(), red)                   # Solver.cs:121-132
+    assert np.array_equal(solver.F(), oracle.build_rhs(m, ni, red))       # Solver.cs:136-152
+    rp, col, val = solver.csr_upper()
+    orp, ocol, oval = K.arrays()
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol)          # pattern: bit-exact
+    assert np.abs(val - oval).max() <= 1e-12 * np.abs(oval).max()
+
+
+def test_regular_grid_structural_pattern(solver, oracle):
+    m = mesh.beam(3, 3, 3)
+    ni, red, K = _assembled(solver, oracle, m)
+    rp, col, val = solver.csr_upper()
+    orp, ocol, oval = K.arrays()
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
+    # mathematically-zero couplings land on 0.0 or ~1e-12 depending on summation order
+    assert np.abs(val - oval).max() <= 1e-12 * np.abs(oval).max()
+
+
+def test_assembly_is_bitwise_deterministic(solver):
+    m = mesh.beam(6, 6, 10, jitter=True)
+    solver.SetModel(m); solver.AssignDOF(); solver.ParallelAssembly_K()
+    v1 = solver.csr_upper()[2]
+    solver.SetModel(m); solver.AssignDOF(); solver.ParallelAssembly_K()
+    assert np.array_equal(v1, solver.csr_upper()[2])
+
+
+def test_spmv_matches_oracle(solver, oracle):
+    m = mesh.beam(4, 3, 6, jitter=True)
+    ni, red, K = _assembled(solver, oracle, m)
+    rng = np.random.default_rng(5)
+    xr = rng.standard_normal(K.n)
+    x_full = oracle.include_bc_dof(red, xr)
+    y_full = solver.spmv(x_full)
+    free = red != -1
+    yo = oracle.sym_spmv(K, xr)
+    assert np.abs(y_full[free] - yo).max() <= 1e-12 * np.abs(yo).max()
+    assert np.array_equal(y_full[~free], x_full[~free])                   # fixed DOFs are identity rows
+
+
+def test_cg_strict_displacements_1e10(solver, oracle):
+    import scipy.sparse.linalg as spl
+    m = mesh.beam(4, 4, 50, tolerance=1e-12)
+    ni, red, K = _assembled(solver, oracle, m)
+    F = oracle.build_rhs(m, ni, red)
+    rep = solver.LinearSolver_CG(merit_check=0, IterMax=2000)
+    xo, orep = oracle.lincg(K, F, oracle.cg_opts(epsf=1e-12, merit_check=0, maxits=2000))
+    assert rep.terminationtype == 1 and orep.terminationtype == 1
+    assert abs(rep.iterationscount - orep.iterationscount) <= 5
+    xg = solver.Exclude_BC_DOF()
+    assert np.linalg.norm(xg - xo) / np.linalg.norm(xo) < 1e-10
+    xs = spl.spsolve(K.to_scipy_full().tocsc(), F)
+    assert np.linalg.norm(xg - xs) / np.linalg.norm(xs) < 1e-10
+    U = solver.Include_BC_DOF()
+    assert np.array_equal(U[red == -1], np.zeros((red == -1).sum()))     # Include_BC_DOF zeros
+    assert np.array_equal(U[red != -1], xg)
+
+
+def test_cg_alglib_semantics(solver, oracle):
+    m = mesh.beam(4, 4, 50, tolerance=1e-8)
+    ni, red, K = _assembled(solver, oracle, m)
+    F = oracle.build_rhs(m, ni, red)
+    rep = solver.LinearSolver_CG()
+    xo, orep = oracle.lincg(K, F, oracle.cg_opts(epsf=1e-8))
+    assert rep.terminationtype == orep.terminationtype == 1
+    assert abs(rep.iterationscount - orep.iterationscount) <= 3
+    assert rep.nmv == 1 + rep.iterationscount + rep.iterationscount // 10
+    assert np.sqrt(rep.r2) <= 1e-8 * rep.bnorm and abs(rep.bnorm - orep.bnorm) <= 1e-12 * orep.bnorm
+    assert np.linalg.norm(solver.Exclude_BC_DOF() - xo) / np.linalg.norm(xo) < 1e-9
+    rep5 = solver.LinearSolver_CG(IterMax=7)
+    assert rep5.terminationtype == 5 and rep5.iterationscount == 7
+    rep7 = solver.LinearSolver_CG(tolerance=1e-30)                        # unreachable -> energy stall
+    assert rep7.terminationtype == 7 and rep7.iterationscount % 10 == 0
+    repz = solver.LinearSolver_CG(zero_based_counter=1)
+    xz, oz = oracle.lincg(K, F, oracle.cg_opts(epsf=1e-8, zero_based_counter=1))
+    assert repz.terminationtype == oz.terminationtype and abs(repz.iterationscount - oz.iterationscount) <= 3
+    m.load_val[:] = 0.0
+    solver.SetModel(m); solver.SetDOF(ni); solver.ParallelAssembly_K()
+    rep0 = solver.LinearSolver_CG()
+    assert rep0.terminationtype == 1 and rep0.iterationscount == 0 and not solver.Include_BC_DOF().any()
+
+
+def test_recovery_stress_1e8(solver, oracle):
+    m = mesh.beam(4, 4, 20, jitter=True, n_parts=2, tolerance=1e-12)
+    ni, red, K = _assembled(solver, oracle, m)
+    solver.LinearSolver_CG(merit_check=0, IterMax=3000)
+    solver.Recovery_Stress()
+    U = solver.Include_BC_DOF()
+    strain, stress = solver.strain_stress()
+    es, ss = oracle.recover(m, ni, U)                                     # same U: isolates R4
+    assert np.abs(strain - es).max() <= 1e-12 * np.abs(es).max()
+    assert np.abs(stress - ss).max() <= 1e-12 * np.abs(ss).max()
+    F = oracle.build_rhs(m, ni, red)
+    xo, _ = oracle.lincg(K, F, oracle.cg_opts(epsf=1e-12, merit_check=0, maxits=3000))
+    es2, ss2 = oracle.recover(m, ni, oracle.include_bc_dof(red, xo))      # end-to-end bar
+    assert np.abs(stress - ss2).max() <= 1e-8 * np.abs(ss2).max()
+    assert np.abs(strain - es2).max() <= 1e-8 * np.abs(es2).max()
+
+
+def test_recovery_g1_and_patch(solver, oracle):
+    m = mesh.beam(3, 3, 5, jitter=True, elem_type=mesh.HEX8_G1, tolerance=1e-10)
+    m.max_iter = 400
+    solver.SetModel(m); ni = solver.AssignDOF(); solver.ParallelAssembly_K()
+    solver.LinearSolver_CG(); solver.Recovery_Stress()
+    U = solver.Include_BC_DOF()
+    strain, stress = solver.strain_stress()
+    es, ss = oracle.recover(m, ni, U)
+    assert np.abs(strain - es).max() <= 1e-12 * max(np.abs(es).max(), 1e-300)
+    assert np.abs(stress - ss).max() <= 1e-12 * max(np.abs(ss).max(), 1e-300)
+    assert np.abs(strain - strain[:, :1, :]).max() == 0.0                 # every node gets the one Gauss value
+
+
+def test_whole_path_driver_matches_oracle(solver, oracle):
+    m = mesh.beam(5, 5, 30, n_parts=3, tolerance=1e-8)
+    r = solver.SolverLinearStatics(m)                                     # Solver.cs:71-217
+    o = oracle.linear_statics(m, oracle.cg_opts(epsf=1e-8))
+    assert np.array_equal(r.node_index, o.node_index)
+    assert r.cg.terminationtype == o.stats.cg.terminationtype
+    assert np.linalg.norm(r.U_full - o.U_full) / np.linalg.norm(o.U_full) < 1e-8
+    assert np.abs(r.stress - o.stress).max() <= 1e-6 * np.abs(o.stress).max()
+    assert r.disp.shape == (m.n_nodes, 3) and np.array_equal(r.disp[m.spc_node], np.zeros((len(m.spc_node), 3)))
+
+
+def test_full_size_properties_100k(solver):
+    """BASELINE config 2 (20x20x250 G2): size-independent checks instead of an oracle run."""
+    m = mesh.workload("beam_100k_g2", tolerance=1e-8)
+    solver.SetModel(m); ni = solver.AssignDOF()
+    assert sorted(ni[:5].tolist()) and len(np.unique(ni)) == m.n_nodes
+    a = solver.ParallelAssembly_K()
+    assert a.n_dof == 332073 and a.n_fixed == 3 * 21 * 21
+    rng = np.random.default_rng(0)
+    x, y = rng.standard_normal(m.n_dof), rng.standard_normal(m.n_dof)
+    Ax, Ay = solver.spmv(x), solver.spmv(y)
+    assert abs(y @ Ax - x @ Ay) <= 1e-11 * abs(y @ Ax)                    # symmetry
+    rep = solver.LinearSolver_CG(merit_check=0, IterMax=5000)
+    assert rep.terminationtype == 1
+    U = solver.Include_BC_DOF()
+    b = np.zeros(m.n_dof)
+    b[3 * ni[m.load_node]] = m.load_val[:, 0]
+    r = b - solver.spmv(U)
+    assert np.linalg.norm(r) <= 1.05e-8 * np.linalg.norm(b)               # true residual at the stated tolerance
+    # rigid translation is in the null space of the unconstrained operator
+    m.spc_node = m.spc_node[:0]; m.spc_val = m.spc_val[:0]
+    solver.SetModel(m); solver.SetDOF(ni); solver.ParallelAssembly_K()
+    t = np.zeros(m.n_dof); t[0::3] = 1.0
+    At = solver.spmv(t)
+    assert np.abs(At).max() <= 1e-9 * np.abs(Ax).max()
+
+
+def test_error_paths(solver):
+    m = mesh.beam(2, 2, 2)
+    s2 = Solver()
+    s2.model = m
+    with pytest.raises(native.StanError) as ei:
+        s2.ParallelAssembly_K()                                           # nothing uploaded yet
+    assert ei.value.code == native.E_STATE
+    s2.close()
+    bad = mesh.beam(2, 2, 2); bad.conn = bad.conn.copy(); bad.conn[0, 0] = 999
+    with pytest.raises(native.StanError) as ei:
+        solver.SetModel(bad)
+    assert ei.value.code == native.E_ARG
+    flat = mesh.beam(2, 2, 2); flat.xyz = flat.xyz.copy(); flat.xyz[:, 2] = 0.0
+    solver.SetModel(flat); solver.AssignDOF()
+    with pytest.raises(native.StanError) as ei:
+        solver.ParallelAssembly_K()                                       # MatrixST.cs:317 throws on det == 0
+    assert ei.value.code == native.E_SINGULAR
+    solver.SetModel(m); solver.AssignDOF(); solver.ParallelAssembly_K()
+    with pytest.raises(native.StanError) as ei:
+        solver.Recovery_Stress()
+    assert ei.value.code == native.E_STATE
+    with pytest.raises(native.StanError):
+        solver.SetDOF(np.zeros(m.n_nodes, np.int32))                      # not a permutation
