@@ -149,6 +149,10 @@ int stan_spmv(stan_handle *h, const double *x_full, double *y_full);
 /* Device time of `reps` back-to-back SpMV launches on the assembled matrix (CUDA events). */
 int stan_time_spmv(stan_handle *h, int32_t reps, double *ms_per_launch, int64_t *bytes_per_launch);
 
+/* CUDA events on the library's own stream, for callers that time a region on the device:
+ * record slot a, run calls, record slot b, then elapsed(a, b) synchronises and returns ms. */
+int stan_event_record(stan_handle *h, int32_t slot);          /* slot in [0, 8) */
+int stan_event_elapsed(stan_handle *h, int32_t slot_a, int32_t slot_b, double *ms);
 /* Kernels launched through this handle so far (bench.py's gpu_launches). */
 int64_t stan_kernel_launches(stan_handle *h);
 

@@ -90,6 +90,7 @@ int stan_destroy(stan_handle *h) {
     h->d_counter.release(s); h->d_ufull.release(s); h->d_strain.release(s); h->d_stress.release(s);
     cudaStreamSynchronize(s);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
+    for (int i = 0; i < 8; i++) if (h->user_ev[i]) cudaEventDestroy(h->user_ev[i]);
     cudaStreamDestroy(h->stream); cudaStreamDestroy(h->comm_stream);
     delete h;
     return STAN_OK;
@@ -367,5 +368,25 @@ int stan_get_partition(stan_handle *h, int64_t *first_row, int64_t *last_row) {
 }
 
 int64_t stan_kernel_launches(stan_handle *h) { return h ? h->launches : 0; }
+
+int stan_event_record(stan_handle *h, int32_t slot) {
+    STAN_TRY(check(h));
+    if (slot < 0 || slot >= 8) { set_error("event slot %d outside [0,8)", slot); return STAN_E_ARG; }
+    if (!h->user_ev[slot]) STAN_CUDA(cudaEventCreate(&h->user_ev[slot]));
+    STAN_CUDA(cudaEventRecord(h->user_ev[slot], h->stream));
+    return STAN_OK;
+}
+
+int stan_event_elapsed(stan_handle *h, int32_t a, int32_t b, double *ms) {
+    STAN_TRY(check(h));
+    if (a < 0 || a >= 8 || b < 0 || b >= 8 || !ms || !h->user_ev[a] || !h->user_ev[b]) {
+        set_error("stan_event_elapsed: slots not recorded"); return STAN_E_ARG;
+    }
+    STAN_CUDA(cudaEventSynchronize(h->user_ev[b]));
+    float f = 0.f;
+    STAN_CUDA(cudaEventElapsedTime(&f, h->user_ev[a], h->user_ev[b]));
+    *ms = f;
+    return STAN_OK;
+}
 
 }  // extern "C"

@@ -75,6 +75,8 @@ SYMBOLS = {
     "stan_spmv": (C.c_int, [_P, _P, _P]),
     "stan_time_spmv": (C.c_int, [_P, _I32, C.POINTER(C.c_double), C.POINTER(_I64)]),
     "stan_kernel_launches": (_I64, [_P]),
+    "stan_event_record": (C.c_int, [_P, _I32]),
+    "stan_event_elapsed": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_double)]),
     "stan_comm_unique_id": (C.c_int, [_P]),
     "stan_comm_init": (C.c_int, [_P, _P]),
     "stan_get_partition": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),

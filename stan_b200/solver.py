@@ -172,6 +172,14 @@ class Solver:
     def kernel_launches(self) -> int:
         return int(self._lib.stan_kernel_launches(self._h))
 
+    def event_record(self, slot: int):
+        native.check(self._lib.stan_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_double()
+        native.check(self._lib.stan_event_elapsed(self._h, a, b, C.byref(ms)))
+        return ms.value
+
     def partition(self):
         a, b = C.c_int64(), C.c_int64()
         native.check(self._lib.stan_get_partition(self._h, C.byref(a), C.byref(b)))
