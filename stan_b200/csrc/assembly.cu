@@ -256,7 +256,7 @@ int upload_fe_tables() {
 int run_assembly(stan_handle *h) {
     cudaStream_t s = h->stream;
     const int64_t nloc = h->row1 - h->row0;
-    STAN_TRY(h->d_vals.alloc((size_t)9 * h->n_blocks, s));
+    STAN_TRY(h->d_vals.alloc((size_t)9 * h->n_blocks + 2, s));   // +2: 16-byte granules of the bulk-copy SpMV
     STAN_TRY(h->d_d2.alloc(3 * nloc, s));
     const size_t smem = (size_t)9 * h->max_group_blocks * sizeof(double);
     if (smem > 200 * 1024) {

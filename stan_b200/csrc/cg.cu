@@ -153,13 +153,13 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partials, u
 // lanes stream 256 B segments of each; the column of entry j is 3*bcol[j/3] + j%3, i.e. one int
 // per nine values.  x is gathered through L1/L2 (neighbouring rows share their columns).
 __device__ __forceinline__ double ld_stream(const double *p) {
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    double v;   // not volatile: the scheduler must be free to batch these ahead of their uses
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
 
 template <bool DOT>
-__global__ void __launch_bounds__(SPMV_THREADS)
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
 k_spmv(int64_t nrows, const int32_t *__restrict__ row_list, const int32_t *__restrict__ brow_ptr,
        const int32_t *__restrict__ bcol, const double *__restrict__ vals, const double *__restrict__ x,
        double *__restrict__ y, double *partials, unsigned int *counter, CgState *st, int slot, int step,
@@ -214,6 +214,148 @@ k_spmv(int64_t nrows, const int32_t *__restrict__ row_list, const int32_t *__res
             const double yv = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
             y[3 * row + lane] = yv;
             if (DOT) dsum += yv * x[3 * row + lane];
+        }
+    }
+    if (DOT) {
+        double v[1] = {dsum};
+        grid_reduce<1>(v, partials, counter, st, slot, step, run_scalar);
+    }
+}
+
+// ---- SpMV, bulk-copy pipeline ------------------------------------------------------------------
+// Persistent CTAs (one per SM).  The matrix is one contiguous stream, so a single elected thread
+// moves it with cp.async.bulk (the TMA engine; UBLKCP in SASS) in chunks of BULK_ROWS block rows —
+// values, block columns and row pointers — into a ring of shared-memory stages, each guarded by
+// an mbarrier that completes on byte count.  Memory-level parallelism is then set by the ring
+// depth (>= 100 KB in flight per SM) instead of by how many loads the compiler keeps outstanding
+// per warp; the 16 consumer warps only touch global memory for the x gather and the y store.
+constexpr int BULK_ROWS = 16;
+constexpr int BULK_WARPS = 16;                         // consumer warps; warp BULK_WARPS is the producer
+constexpr int BULK_THREADS = 32 * (BULK_WARPS + 1);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+struct BulkLayout {          // per-stage byte offsets inside dynamic shared memory
+    int vals_off, cols_off, rp_off, stage_bytes, stages;
+};
+
+template <bool DOT>
+__global__ void __launch_bounds__(BULK_THREADS, 1)
+k_spmv_bulk(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
+            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, BulkLayout L,
+            double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar) {
+    if (st && st->done) return;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ __align__(8) uint64_t s_full[8], s_empty[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = L.stages;
+    const int64_t nchunks = (nrows + BULK_ROWS - 1) / BULK_ROWS;
+    const int64_t my_n = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0) {
+        for (int i = 0; i < S; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], BULK_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double dsum = 0.0;
+    if (warp == BULK_WARPS) {
+        // ---- producer: one lane streams this CTA's chunks through the ring ----
+        if (lane == 0) {
+            for (int64_t i = 0; i < my_n; i++) {
+                const int stg = (int)(i % S);
+                if (i >= S) mbar_wait(&s_empty[stg], (uint32_t)(((i / S) - 1) & 1));
+                const int64_t c = blockIdx.x + i * (int64_t)gridDim.x;
+                const int64_t r0 = c * BULK_ROWS, r1 = (r0 + BULK_ROWS < nrows) ? r0 + BULK_ROWS : nrows;
+                unsigned char *base = s_raw + (size_t)stg * L.stage_bytes;
+                const int64_t b0 = brow_ptr[r0], b1 = brow_ptr[r1];
+                const int64_t voff = 72 * b0, voff_al = voff & ~(int64_t)15;
+                const uint32_t vbytes = (uint32_t)(((voff - voff_al) + 72 * (b1 - b0) + 15) & ~(int64_t)15);
+                const int64_t coff = 4 * b0, coff_al = coff & ~(int64_t)15;
+                const uint32_t cbytes = (uint32_t)(((coff - coff_al) + 4 * (b1 - b0) + 15) & ~(int64_t)15);
+                const uint32_t rbytes = (uint32_t)((4 * (r1 - r0 + 1) + 15) & ~(int64_t)15);   // r0 % 16 == 0
+                mbar_expect_tx(&s_full[stg], vbytes + cbytes + rbytes);
+                bulk_g2s(base + L.vals_off, (const unsigned char *)vals + voff_al, vbytes, &s_full[stg]);
+                bulk_g2s(base + L.cols_off, (const unsigned char *)bcol + coff_al, cbytes, &s_full[stg]);
+                bulk_g2s(base + L.rp_off, (const unsigned char *)(brow_ptr + r0), rbytes, &s_full[stg]);
+            }
+        }
+    } else {
+        // ---- consumers: one block row per warp and chunk ----
+        for (int64_t i = 0; i < my_n; i++) {
+            const int stg = (int)(i % S);
+            mbar_wait(&s_full[stg], (uint32_t)((i / S) & 1));
+            const unsigned char *base = s_raw + (size_t)stg * L.stage_bytes;
+            const int32_t *rp = reinterpret_cast<const int32_t *>(base + L.rp_off);
+            const int64_t c = blockIdx.x + i * (int64_t)gridDim.x;
+            const int64_t r0 = c * BULK_ROWS;
+            const int nr = (int)((nrows - r0) < BULK_ROWS ? (nrows - r0) : BULK_ROWS);
+            const int b0 = rp[0];
+            const double *cv = reinterpret_cast<const double *>(base + L.vals_off) + ((9 * (int64_t)b0) & 1);
+            const int32_t *cc = reinterpret_cast<const int32_t *>(base + L.cols_off) + (b0 & 3);
+            for (int lr = warp; lr < nr; lr += BULK_WARPS) {
+                const int s = rp[lr] - b0;
+                const int len = 3 * (rp[lr + 1] - rp[lr]);
+                const double *v0 = cv + 9 * s, *v1 = v0 + len, *v2 = v1 + len;
+                const int32_t *cols = cc + s;
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+                for (int j0 = 0; j0 < len; j0 += 96) {
+                    double xv[3];
+                    int jj[3];
+#pragma unroll
+                    for (int u = 0; u < 3; u++) {
+                        const int j = j0 + lane + 32 * u;
+                        jj[u] = j < len ? j : len - 1;
+                        const int blk = jj[u] / 3;
+                        const double xg = x[3 * (int64_t)cols[blk] + (jj[u] - 3 * blk)];
+                        xv[u] = j < len ? xg : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 3; u++) {
+                        a0 += v0[jj[u]] * xv[u];
+                        a1 += v1[jj[u]] * xv[u];
+                        a2 += v2[jj[u]] * xv[u];
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                }
+                if (lane < 3) {
+                    const double yv = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+                    const int64_t row = r0 + lr;
+                    y[3 * row + lane] = yv;
+                    if (DOT) dsum += yv * x[3 * row + lane];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[stg]);          // this warp is done with the stage
         }
     }
     if (DOT) {
@@ -310,16 +452,81 @@ int64_t spmv_algorithmic_bytes(const stan_handle *h) {
     return 72 * h->n_blocks + 4 * h->n_blocks + nloc * (4 + 24 + 24);
 }
 
-static int spmv_grid(const stan_handle *h, int64_t nrows) {
-    int64_t want = (nrows + SPMV_WARPS - 1) / SPMV_WARPS;
-    int64_t cap = (int64_t)h->sm_count * 8;
+// grids are sized to exactly one resident wave (SM count x CTAs that fit per SM) and loop
+template <typename K>
+static int resident_grid(const stan_handle *h, K kernel, int threads, size_t smem, int64_t want) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    const int64_t cap = (int64_t)h->sm_count * per_sm;
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
 static int vec_grid(const stan_handle *h, int64_t n) {
-    int64_t want = (n + VEC_THREADS * 4 - 1) / (VEC_THREADS * 4);
-    int64_t cap = (int64_t)h->sm_count * 8;
-    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+    return resident_grid(h, k_update, VEC_THREADS, 0, (n + VEC_THREADS * 2 - 1) / (VEC_THREADS * 2));
+}
+
+static int spmv_variant() {
+    static int v = -1;
+    if (v < 0) {
+        // 0 = warp-per-row LDG kernel (default: 5.0 TB/s on the 10M beam, profiles/r01_spmv_variants.md),
+        // 1 = bulk-copy (TMA) pipeline (4.0 TB/s: consumer-latency bound, kept for further tuning)
+        const char *e = getenv("STAN_SPMV");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+static BulkLayout bulk_layout(const stan_handle *h) {
+    BulkLayout L;
+    const int mb = h->max_group16 > 0 ? h->max_group16 : 1;
+    auto up = [](int v) { return (v + 127) & ~127; };
+    L.vals_off = 0;
+    L.cols_off = up(72 * mb + 16);
+    L.rp_off = L.cols_off + up(4 * mb + 32);
+    L.stage_bytes = L.rp_off + 128;
+    int st = (int)((200 * 1024) / L.stage_bytes);
+    L.stages = st > 8 ? 8 : st;
+    return L;
+}
+
+struct SpmvPlan { int variant, grid; BulkLayout L; size_t smem; };
+
+static int spmv_plan(const stan_handle *h, int64_t nrows, SpmvPlan *p) {
+    p->variant = spmv_variant();
+    p->L = bulk_layout(h);
+    if (p->variant == 1 && p->L.stages < 2) p->variant = 0;   // rows too wide for the shared-memory ring
+    if (p->variant == 1) {
+        p->smem = (size_t)p->L.stages * p->L.stage_bytes;
+        STAN_CUDA(cudaFuncSetAttribute(k_spmv_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+        STAN_CUDA(cudaFuncSetAttribute(k_spmv_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+        const int64_t nchunks = (nrows + BULK_ROWS - 1) / BULK_ROWS;
+        p->grid = (int)(nchunks < h->sm_count ? (nchunks > 0 ? nchunks : 1) : h->sm_count);
+    } else {
+        p->smem = 0;
+        p->grid = resident_grid(h, k_spmv<true>, SPMV_THREADS, 0, (nrows + SPMV_WARPS - 1) / SPMV_WARPS);
+    }
+    return STAN_OK;
+}
+
+static void launch_spmv(const stan_handle *h, const SpmvPlan &p, bool dot, int64_t nrows, const double *in, double *out,
+                        double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar,
+                        cudaStream_t s) {
+    if (p.variant == 1) {
+        if (dot)
+            k_spmv_bulk<true><<<p.grid, BULK_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
+                                                                   p.L, partials, counter, st, slot, step, run_scalar);
+        else
+            k_spmv_bulk<false><<<p.grid, BULK_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
+                                                                    p.L, partials, counter, st, slot, step, run_scalar);
+    } else {
+        if (dot)
+            k_spmv<true><<<p.grid, SPMV_THREADS, 0, s>>>(nrows, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
+                                                         partials, counter, st, slot, step, run_scalar);
+        else
+            k_spmv<false><<<p.grid, SPMV_THREADS, 0, s>>>(nrows, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
+                                                          partials, counter, st, slot, step, run_scalar);
+    }
 }
 
 int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
@@ -336,7 +543,9 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
 
     STAN_TRY(h->d_x.alloc(nx, s)); STAN_TRY(h->d_xalt.alloc(nx, s));
     STAN_TRY(h->d_r.alloc(n, s)); STAN_TRY(h->d_p.alloc(nx, s)); STAN_TRY(h->d_mv.alloc(n, s));
-    const int gv = vec_grid(h, n), gs = spmv_grid(h, nloc);
+    SpmvPlan plan;
+    STAN_TRY(spmv_plan(h, nloc, &plan));
+    const int gv = vec_grid(h, n), gs = plan.grid;
     const int gmax = gv > gs ? gv : gs;
     STAN_TRY(h->d_partials.alloc((size_t)gmax * 4, s));
     STAN_TRY(h->d_state.alloc(1, s));
@@ -376,8 +585,7 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
         if (multi) STAN_TRY(comm_halo_exchange(h, in, s));
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (timek) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
-        k_spmv<true><<<gs, SPMV_THREADS, 0, s>>>(nloc, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in,
-                                                 h->d_mv.p, h->d_partials.p, h->d_counter.p + 2, st, slot, step, single);
+        launch_spmv(h, plan, true, nloc, in, h->d_mv.p, h->d_partials.p, h->d_counter.p + 2, st, slot, step, single, s);
         if (timek) { cudaEventRecord(e1, s); evs.push_back(e0); evs.push_back(e1); }
         launches++; spmv_launches++;
         if (step != SC_NONE) STAN_TRY(reduce_tail(step));
@@ -459,9 +667,9 @@ int spmv_full(stan_handle *h, const double *x_full, double *y_full) {
     DevBuf<double> x, y;
     STAN_TRY(x.alloc(n, s)); STAN_TRY(y.alloc(n, s));
     STAN_CUDA(cudaMemcpyAsync(x.p, x_full, n * sizeof(double), cudaMemcpyHostToDevice, s));
-    k_spmv<false><<<spmv_grid(h, h->n_nodes), SPMV_THREADS, 0, s>>>(h->n_nodes, nullptr, h->d_brow_ptr.p,
-                                                                     h->bcol_x, h->d_vals.p, x.p, y.p, nullptr,
-                                                                     nullptr, nullptr, 0, SC_NONE, false);
+    SpmvPlan plan;
+    STAN_TRY(spmv_plan(h, h->n_nodes, &plan));
+    launch_spmv(h, plan, false, h->n_nodes, x.p, y.p, nullptr, nullptr, nullptr, 0, SC_NONE, false, s);
     STAN_CUDA(cudaGetLastError());
     STAN_CUDA(cudaMemcpyAsync(y_full, y.p, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     STAN_CUDA(cudaStreamSynchronize(s));
@@ -476,14 +684,13 @@ int time_spmv(stan_handle *h, int reps, double *ms_out, int64_t *bytes) {
     DevBuf<double> x, y;
     STAN_TRY(x.alloc(nx, s)); STAN_TRY(y.alloc(3 * nloc, s));
     STAN_CUDA(cudaMemsetAsync(x.p, 0, nx * sizeof(double), s));
-    const int gs = spmv_grid(h, nloc);
+    SpmvPlan plan;
+    STAN_TRY(spmv_plan(h, nloc, &plan));
     for (int w = 0; w < 3; w++)
-        k_spmv<false><<<gs, SPMV_THREADS, 0, s>>>(nloc, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, x.p, y.p,
-                                                  nullptr, nullptr, nullptr, 0, SC_NONE, false);
+        launch_spmv(h, plan, false, nloc, x.p, y.p, nullptr, nullptr, nullptr, 0, SC_NONE, false, s);
     STAN_CUDA(cudaEventRecord(h->ev2, s));
     for (int r = 0; r < reps; r++)
-        k_spmv<false><<<gs, SPMV_THREADS, 0, s>>>(nloc, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, x.p, y.p,
-                                                  nullptr, nullptr, nullptr, 0, SC_NONE, false);
+        launch_spmv(h, plan, false, nloc, x.p, y.p, nullptr, nullptr, nullptr, 0, SC_NONE, false, s);
     STAN_CUDA(cudaEventRecord(h->ev3, s));
     STAN_CUDA(cudaStreamSynchronize(s));
     STAN_CUDA(cudaGetLastError());

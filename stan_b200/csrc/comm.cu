@@ -180,7 +180,7 @@ int comm_build_halo(stan_handle *h) {
         cudaFreeAsync(tmp, s);
         STAN_CUDA(e);
     }
-    STAN_TRY(h->d_bcol_loc.alloc(h->n_blocks, s));
+    STAN_TRY(h->d_bcol_loc.alloc((size_t)h->n_blocks + 4, s));
     k_localize_cols<<<div_up(h->n_blocks, 256), 256, 0, s>>>(h->n_blocks, h->d_bcol.p, h->row0, h->row1, slot.p,
                                                              h->d_bcol_loc.p);
     h->bcol_x = h->d_bcol_loc.p;

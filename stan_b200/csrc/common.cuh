@@ -130,6 +130,7 @@ struct stan_handle {
     stan::DevBuf<int32_t> d_err;        // device error flags
     int64_t n_blocks = 0, n_fixed = 0, nnz_upper = 0;
     int32_t max_group_blocks = 0;       // max blocks in a 32-row group (assembly smem sizing)
+    int32_t max_group16 = 0;            // max blocks in a 16-row group (SpMV stage sizing)
 
     // ---- CG work vectors (3*(nloc+n_halo) where halo is needed) ----
     stan::DevBuf<double> d_x, d_xalt, d_r, d_p, d_mv, d_partials;

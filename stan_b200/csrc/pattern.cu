@@ -203,7 +203,7 @@ int build_system_pattern(stan_handle *h) {
     k_inc_sort<<<div_up(nloc, T), T, 0, s>>>(nloc, h->d_inc_ptr.p, h->d_inc.p);
 
     // block rows
-    STAN_TRY(h->d_brow_ptr.alloc(nloc + 1, s));
+    STAN_TRY(h->d_brow_ptr.alloc(nloc + 1 + 4, s));      // +4: the bulk-copy SpMV reads 16-byte granules
     STAN_CUDA(cudaMemsetAsync(cnt.p, 0, (nloc + 1) * sizeof(int32_t), s));
     k_row_neighbors<false><<<div_up(nloc, 128), 128, 0, s>>>(nloc, h->d_inc_ptr.p, h->d_inc.p, h->d_conn.p,
                                                              h->d_node_index.p, cnt.p, nullptr, nullptr, h->d_err.p);
@@ -219,11 +219,12 @@ int build_system_pattern(stan_handle *h) {
         return STAN_E_CAPACITY;
     }
     h->n_blocks = nblk;
-    STAN_TRY(h->d_bcol.alloc(nblk, s));
+    STAN_TRY(h->d_bcol.alloc((size_t)nblk + 4, s));
     k_row_neighbors<true><<<div_up(nloc, 128), 128, 0, s>>>(nloc, h->d_inc_ptr.p, h->d_inc.p, h->d_conn.p,
                                                             h->d_node_index.p, nullptr, h->d_brow_ptr.p, h->d_bcol.p,
                                                             h->d_err.p);
     k_group_max<<<div_up(div_up(nloc, 32), T), T, 0, s>>>(nloc, 32, h->d_brow_ptr.p, h->d_err.p + 1);
+    k_group_max<<<div_up(div_up(nloc, 16), T), T, 0, s>>>(nloc, 16, h->d_brow_ptr.p, h->d_err.p + 3);
     cnt.release(s);
 
     // SPC flags and nDOF_reduction over the global DOF range
@@ -254,6 +255,7 @@ int build_system_pattern(stan_handle *h) {
         STAN_CUDA(cudaStreamSynchronize(s));
         h->n_fixed = nfix;
         h->max_group_blocks = herr[1];
+        h->max_group16 = herr[3];
     }
     h->launches += 12;
     return STAN_OK;
