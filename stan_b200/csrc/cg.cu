@@ -158,8 +158,8 @@ __device__ __forceinline__ double ld_stream(const double *p) {
     return v;
 }
 
-template <bool DOT>
-__global__ void __launch_bounds__(SPMV_THREADS, 4)
+template <bool DOT, int MINB>
+__global__ void __launch_bounds__(SPMV_THREADS, MINB)
 k_spmv(int64_t nrows, const int32_t *__restrict__ row_list, const int32_t *__restrict__ brow_ptr,
        const int32_t *__restrict__ bcol, const double *__restrict__ vals, const double *__restrict__ x,
        double *__restrict__ y, double *partials, unsigned int *counter, CgState *st, int slot, int step,
@@ -265,7 +265,7 @@ struct BulkLayout {          // per-stage byte offsets inside dynamic shared mem
 };
 
 template <bool DOT>
-__global__ void __launch_bounds__(BULK_THREADS, 1)
+__global__ void __launch_bounds__(BULK_THREADS)
 k_spmv_bulk(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
             const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, BulkLayout L,
             double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar) {
@@ -305,40 +305,57 @@ k_spmv_bulk(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t *
             }
         }
     } else {
-        // ---- consumers: one block row per warp and chunk ----
-        for (int64_t i = 0; i < my_n; i++) {
+        // ---- consumers: one block row per warp and chunk; the x gather of the next chunk's row is
+        // issued before the current row is reduced, so its L2 latency hides behind useful work ----
+        struct RowCtx { const double *v0; int len, jj[3]; double xv[3]; int64_t row; bool have; };
+        auto fetch = [&](int64_t i, RowCtx &r) {
             const int stg = (int)(i % S);
             mbar_wait(&s_full[stg], (uint32_t)((i / S) & 1));
             const unsigned char *base = s_raw + (size_t)stg * L.stage_bytes;
             const int32_t *rp = reinterpret_cast<const int32_t *>(base + L.rp_off);
-            const int64_t c = blockIdx.x + i * (int64_t)gridDim.x;
-            const int64_t r0 = c * BULK_ROWS;
+            const int64_t r0 = (blockIdx.x + i * (int64_t)gridDim.x) * BULK_ROWS;
             const int nr = (int)((nrows - r0) < BULK_ROWS ? (nrows - r0) : BULK_ROWS);
+            r.have = warp < nr;
+            if (!r.have) return;
             const int b0 = rp[0];
-            const double *cv = reinterpret_cast<const double *>(base + L.vals_off) + ((9 * (int64_t)b0) & 1);
-            const int32_t *cc = reinterpret_cast<const int32_t *>(base + L.cols_off) + (b0 & 3);
-            for (int lr = warp; lr < nr; lr += BULK_WARPS) {
-                const int s = rp[lr] - b0;
-                const int len = 3 * (rp[lr + 1] - rp[lr]);
-                const double *v0 = cv + 9 * s, *v1 = v0 + len, *v2 = v1 + len;
-                const int32_t *cols = cc + s;
+            const int sblk = rp[warp] - b0;
+            r.len = 3 * (rp[warp + 1] - rp[warp]);
+            r.row = r0 + warp;
+            r.v0 = reinterpret_cast<const double *>(base + L.vals_off) + ((9 * (int64_t)b0) & 1) + 9 * sblk;
+            const int32_t *cols = reinterpret_cast<const int32_t *>(base + L.cols_off) + (b0 & 3) + sblk;
+#pragma unroll
+            for (int u = 0; u < 3; u++) {
+                const int j = lane + 32 * u;
+                r.jj[u] = j < r.len ? j : r.len - 1;
+                const int blk = r.jj[u] / 3;
+                const double xg = x[3 * (int64_t)cols[blk] + (r.jj[u] - 3 * blk)];
+                r.xv[u] = j < r.len ? xg : 0.0;
+            }
+        };
+        RowCtx cur, nxt;
+        cur.have = nxt.have = false;
+        if (my_n > 0) fetch(0, cur);
+        for (int64_t i = 0; i < my_n; i++) {
+            const int stg = (int)(i % S);
+            if (i + 1 < my_n) fetch(i + 1, nxt);
+            if (cur.have) {
+                const double *v0 = cur.v0, *v1 = v0 + cur.len, *v2 = v1 + cur.len;
                 double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-                for (int j0 = 0; j0 < len; j0 += 96) {
-                    double xv[3];
-                    int jj[3];
 #pragma unroll
-                    for (int u = 0; u < 3; u++) {
-                        const int j = j0 + lane + 32 * u;
-                        jj[u] = j < len ? j : len - 1;
-                        const int blk = jj[u] / 3;
-                        const double xg = x[3 * (int64_t)cols[blk] + (jj[u] - 3 * blk)];
-                        xv[u] = j < len ? xg : 0.0;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 3; u++) {
-                        a0 += v0[jj[u]] * xv[u];
-                        a1 += v1[jj[u]] * xv[u];
-                        a2 += v2[jj[u]] * xv[u];
+                for (int u = 0; u < 3; u++) {
+                    a0 += v0[cur.jj[u]] * cur.xv[u];
+                    a1 += v1[cur.jj[u]] * cur.xv[u];
+                    a2 += v2[cur.jj[u]] * cur.xv[u];
+                }
+                if (cur.len > 96) {                             // rows wider than 32 blocks: rest without prefetch
+                    const unsigned char *base = s_raw + (size_t)stg * L.stage_bytes;
+                    const int32_t *rp = reinterpret_cast<const int32_t *>(base + L.rp_off);
+                    const int b0 = rp[0];
+                    const int32_t *cols = reinterpret_cast<const int32_t *>(base + L.cols_off) + (b0 & 3) + (rp[warp] - b0);
+                    for (int j = 96 + lane; j < cur.len; j += 32) {
+                        const int blk = j / 3;
+                        const double xg = x[3 * (int64_t)cols[blk] + (j - 3 * blk)];
+                        a0 += v0[j] * xg; a1 += v1[j] * xg; a2 += v2[j] * xg;
                     }
                 }
 #pragma unroll
@@ -349,13 +366,120 @@ k_spmv_bulk(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t *
                 }
                 if (lane < 3) {
                     const double yv = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
-                    const int64_t row = r0 + lr;
-                    y[3 * row + lane] = yv;
-                    if (DOT) dsum += yv * x[3 * row + lane];
+                    y[3 * cur.row + lane] = yv;
+                    if (DOT) dsum += yv * x[3 * cur.row + lane];
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[stg]);          // this warp is done with the stage
+            cur = nxt;
+        }
+    }
+    if (DOT) {
+        double v[1] = {dsum};
+        grid_reduce<1>(v, partials, counter, st, slot, step, run_scalar);
+    }
+}
+
+// ---- SpMV, bulk-copy tiles with one thread per scalar row ---------------------------------------
+// ncu on the warp-per-row kernels (profiles/r01_spmv.md) shows both pinned at ~5.0 TB/s by the L1
+// data pipe: ~100 wavefronts per block row (27 for misaligned value loads, ~24 for the x gather,
+// 30 for the shuffle reduction).  Here the TMA engine stages TILE_ROWS block rows in shared memory
+// and every thread owns one scalar row: values and columns come from shared memory conflict-free,
+// the row sum needs no shuffles, x is gathered through L1 where the lanes of a warp (consecutive
+// rows) hit the same few lines, and y is stored coalesced.  ~45 wavefronts and ~35 instructions
+// per block row.  G consumer groups each own one stage of the ring; a producer warp refills a
+// stage as soon as its group releases it.
+template <bool DOT, int TILE_ROWS, int GROUPS>
+__global__ void __launch_bounds__(32 * (GROUPS * ((3 * TILE_ROWS + 31) / 32) + 1))
+k_spmv_tile(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
+            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, BulkLayout L,
+            double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar) {
+    if (st && st->done) return;
+    constexpr int GW = (3 * TILE_ROWS + 31) / 32;          // warps per consumer group
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ __align__(8) uint64_t s_full[GROUPS], s_empty[GROUPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t nchunks = (nrows + TILE_ROWS - 1) / TILE_ROWS;
+    const int64_t my_n = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0) {
+        for (int i = 0; i < GROUPS; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], GW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double dsum = 0.0;
+    if (warp == GROUPS * GW) {
+        if (lane == 0) {                                   // ---- producer ----
+            for (int64_t i = 0; i < my_n; i++) {
+                const int g = (int)(i % GROUPS);
+                const int64_t k = i / GROUPS;
+                if (k > 0) mbar_wait(&s_empty[g], (uint32_t)((k - 1) & 1));
+                const int64_t r0 = (blockIdx.x + i * (int64_t)gridDim.x) * TILE_ROWS;
+                const int64_t r1 = (r0 + TILE_ROWS < nrows) ? r0 + TILE_ROWS : nrows;
+                unsigned char *base = s_raw + (size_t)g * L.stage_bytes;
+                const int64_t b0 = brow_ptr[r0], b1 = brow_ptr[r1];
+                const int64_t voff = 72 * b0, voff_al = voff & ~(int64_t)15;
+                const uint32_t vbytes = (uint32_t)(((voff - voff_al) + 72 * (b1 - b0) + 15) & ~(int64_t)15);
+                const int64_t coff = 4 * b0, coff_al = coff & ~(int64_t)15;
+                const uint32_t cbytes = (uint32_t)(((coff - coff_al) + 4 * (b1 - b0) + 15) & ~(int64_t)15);
+                const uint32_t rbytes = (uint32_t)((4 * (r1 - r0 + 1) + 15) & ~(int64_t)15);   // TILE_ROWS % 4 == 0
+                mbar_expect_tx(&s_full[g], vbytes + cbytes + rbytes);
+                bulk_g2s(base + L.vals_off, (const unsigned char *)vals + voff_al, vbytes, &s_full[g]);
+                bulk_g2s(base + L.cols_off, (const unsigned char *)bcol + coff_al, cbytes, &s_full[g]);
+                bulk_g2s(base + L.rp_off, (const unsigned char *)(brow_ptr + r0), rbytes, &s_full[g]);
+            }
+        }
+    } else {
+        const int g = warp / GW;                           // ---- consumers ----
+        const int t = tid - g * GW * 32;                   // scalar row of the tile owned by this thread
+        const int br = t / 3, a = t - 3 * br;
+        const unsigned char *base = s_raw + (size_t)g * L.stage_bytes;
+        const int32_t *rp = reinterpret_cast<const int32_t *>(base + L.rp_off);
+        for (int64_t i = g, k = 0; i < my_n; i += GROUPS, k++) {
+            mbar_wait(&s_full[g], (uint32_t)(k & 1));
+            const int64_t r0 = (blockIdx.x + i * (int64_t)gridDim.x) * TILE_ROWS;
+            const int nr = (int)((nrows - r0) < TILE_ROWS ? (nrows - r0) : TILE_ROWS);
+            if (br < nr) {
+                const int b0 = rp[0];
+                const int sblk = rp[br] - b0, nb = rp[br + 1] - rp[br];
+                const double *v = reinterpret_cast<const double *>(base + L.vals_off) + ((9 * (int64_t)b0) & 1) +
+                                  9 * sblk + a * 3 * nb;
+                const int32_t *cols = reinterpret_cast<const int32_t *>(base + L.cols_off) + (b0 & 3) + sblk;
+                // batches of 9 blocks: all column and x loads of a batch are issued before the first
+                // FMA, and three accumulators keep the DFMA chain short
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+                int c = 0;
+                for (; c + 9 <= nb; c += 9) {
+                    int q[9];
+                    double xa[9], xb[9], xc[9];
+#pragma unroll
+                    for (int u = 0; u < 9; u++) q[u] = cols[c + u];
+#pragma unroll
+                    for (int u = 0; u < 9; u++) {
+                        const double *xp = x + 3 * (int64_t)q[u];
+                        xa[u] = xp[0]; xb[u] = xp[1]; xc[u] = xp[2];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 9; u++) {
+                        acc0 += v[3 * (c + u)] * xa[u];
+                        acc1 += v[3 * (c + u) + 1] * xb[u];
+                        acc2 += v[3 * (c + u) + 2] * xc[u];
+                    }
+                }
+                for (; c < nb; c++) {
+                    const double *xp = x + 3 * (int64_t)cols[c];
+                    acc0 += v[3 * c] * xp[0];
+                    acc1 += v[3 * c + 1] * xp[1];
+                    acc2 += v[3 * c + 2] * xp[2];
+                }
+                const double acc = (acc0 + acc1) + acc2;
+                const int64_t dof = 3 * (r0 + br) + a;
+                y[dof] = acc;
+                if (DOT) dsum += acc * x[dof];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[g]);
         }
     }
     if (DOT) {
@@ -477,34 +601,62 @@ static int spmv_variant() {
     return v;
 }
 
-static BulkLayout bulk_layout(const stan_handle *h) {
+static BulkLayout bulk_layout(const stan_handle *h, int tile_rows = 16) {
     BulkLayout L;
-    const int mb = h->max_group16 > 0 ? h->max_group16 : 1;
+    int mb = tile_rows == 32 ? h->max_group_blocks : h->max_group16;
+    if (mb < 1) mb = 1;
     auto up = [](int v) { return (v + 127) & ~127; };
     L.vals_off = 0;
     L.cols_off = up(72 * mb + 16);
     L.rp_off = L.cols_off + up(4 * mb + 32);
-    L.stage_bytes = L.rp_off + 128;
-    int st = (int)((200 * 1024) / L.stage_bytes);
+    L.stage_bytes = L.rp_off + 256;                       // row pointers: up to 33 ints rounded to 16 B
+    static int ctas = getenv("STAN_BULK_CTAS") ? atoi(getenv("STAN_BULK_CTAS")) : 1;
+    int st = (int)((200 * 1024 / ctas) / L.stage_bytes);
     L.stages = st > 8 ? 8 : st;
     return L;
 }
 
-struct SpmvPlan { int variant, grid; BulkLayout L; size_t smem; };
+struct SpmvPlan { int variant, grid, minb; BulkLayout L; size_t smem; };
 
 static int spmv_plan(const stan_handle *h, int64_t nrows, SpmvPlan *p) {
     p->variant = spmv_variant();
     p->L = bulk_layout(h);
     if (p->variant == 1 && p->L.stages < 2) p->variant = 0;   // rows too wide for the shared-memory ring
+    if (p->variant == 2 || p->variant == 3) {                 // 2: 16-row tiles x 6 groups, 3: 32-row tiles x 3 groups
+        const int tr = p->variant == 2 ? 16 : 32, groups = p->variant == 2 ? 6 : 3;
+        p->L = bulk_layout(h, tr);
+        p->L.stages = groups;
+        p->smem = (size_t)groups * p->L.stage_bytes;
+        if (p->smem > 220 * 1024) p->variant = 0;
+        else {
+            if (tr == 16) {
+                STAN_CUDA(cudaFuncSetAttribute(k_spmv_tile<true, 16, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+                STAN_CUDA(cudaFuncSetAttribute(k_spmv_tile<false, 16, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+            } else {
+                STAN_CUDA(cudaFuncSetAttribute(k_spmv_tile<true, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+                STAN_CUDA(cudaFuncSetAttribute(k_spmv_tile<false, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+            }
+            const int64_t nchunks = (nrows + tr - 1) / tr;
+            p->grid = (int)(nchunks < h->sm_count ? (nchunks > 0 ? nchunks : 1) : h->sm_count);
+            return STAN_OK;
+        }
+    }
     if (p->variant == 1) {
         p->smem = (size_t)p->L.stages * p->L.stage_bytes;
         STAN_CUDA(cudaFuncSetAttribute(k_spmv_bulk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
         STAN_CUDA(cudaFuncSetAttribute(k_spmv_bulk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
         const int64_t nchunks = (nrows + BULK_ROWS - 1) / BULK_ROWS;
-        p->grid = (int)(nchunks < h->sm_count ? (nchunks > 0 ? nchunks : 1) : h->sm_count);
+        const int64_t cap = (int64_t)h->sm_count * (getenv("STAN_BULK_CTAS") ? atoi(getenv("STAN_BULK_CTAS")) : 1);
+        p->grid = (int)(nchunks < cap ? (nchunks > 0 ? nchunks : 1) : cap);
     } else {
         p->smem = 0;
-        p->grid = resident_grid(h, k_spmv<true>, SPMV_THREADS, 0, (nrows + SPMV_WARPS - 1) / SPMV_WARPS);
+        // 6 CTAs/SM (<= 40 registers, 48 warps): 5.27 TB/s vs 5.00 at 4 CTAs/SM on the 10M beam
+        static int minb = getenv("STAN_SPMV_MINB") ? atoi(getenv("STAN_SPMV_MINB")) : 6;
+        p->minb = minb;
+        const int64_t want = (nrows + SPMV_WARPS - 1) / SPMV_WARPS;
+        p->grid = minb == 8 ? resident_grid(h, k_spmv<true, 8>, SPMV_THREADS, 0, want)
+                : minb == 6 ? resident_grid(h, k_spmv<true, 6>, SPMV_THREADS, 0, want)
+                            : resident_grid(h, k_spmv<true, 4>, SPMV_THREADS, 0, want);
     }
     return STAN_OK;
 }
@@ -512,6 +664,12 @@ static int spmv_plan(const stan_handle *h, int64_t nrows, SpmvPlan *p) {
 static void launch_spmv(const stan_handle *h, const SpmvPlan &p, bool dot, int64_t nrows, const double *in, double *out,
                         double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar,
                         cudaStream_t s) {
+#define STAN_LAUNCH_TILE(D, R, G)                                                                                  \
+    k_spmv_tile<D, R, G><<<p.grid, 32 * (G * ((3 * R + 31) / 32) + 1), p.smem, s>>>(                               \
+        nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out, p.L, partials, counter, st, slot, step, run_scalar)
+    if (p.variant == 2) { if (dot) STAN_LAUNCH_TILE(true, 16, 6); else STAN_LAUNCH_TILE(false, 16, 6); return; }
+    if (p.variant == 3) { if (dot) STAN_LAUNCH_TILE(true, 32, 3); else STAN_LAUNCH_TILE(false, 32, 3); return; }
+#undef STAN_LAUNCH_TILE
     if (p.variant == 1) {
         if (dot)
             k_spmv_bulk<true><<<p.grid, BULK_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
@@ -520,12 +678,13 @@ static void launch_spmv(const stan_handle *h, const SpmvPlan &p, bool dot, int64
             k_spmv_bulk<false><<<p.grid, BULK_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
                                                                     p.L, partials, counter, st, slot, step, run_scalar);
     } else {
-        if (dot)
-            k_spmv<true><<<p.grid, SPMV_THREADS, 0, s>>>(nrows, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
-                                                         partials, counter, st, slot, step, run_scalar);
-        else
-            k_spmv<false><<<p.grid, SPMV_THREADS, 0, s>>>(nrows, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
-                                                          partials, counter, st, slot, step, run_scalar);
+#define STAN_LAUNCH_LDG(D, M)                                                                                     \
+    k_spmv<D, M><<<p.grid, SPMV_THREADS, 0, s>>>(nrows, nullptr, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out, \
+                                                 partials, counter, st, slot, step, run_scalar)
+        if (p.minb == 8) { if (dot) STAN_LAUNCH_LDG(true, 8); else STAN_LAUNCH_LDG(false, 8); }
+        else if (p.minb == 6) { if (dot) STAN_LAUNCH_LDG(true, 6); else STAN_LAUNCH_LDG(false, 6); }
+        else { if (dot) STAN_LAUNCH_LDG(true, 4); else STAN_LAUNCH_LDG(false, 4); }
+#undef STAN_LAUNCH_LDG
     }
 }
 
