@@ -1,0 +1,42 @@
+"""Multi-GPU parity: the partitioned solve (one process per GPU, NCCL halo + all-reduce) against the
+single-GPU solve of the same model on the same device.  Launch with torchrun:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multi_gpu_check.py [nx ny nz]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from stan_b200 import mesh  # noqa: E402
+from stan_b200.solver import Solver, comm_unique_id  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dims = [int(v) for v in sys.argv[1:4]] if len(sys.argv) >= 4 else [12, 10, 60]
+m = mesh.beam(*dims, jitter=True, n_parts=2, tolerance=1e-9)
+uid = [comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+
+multi = Solver(device=local, rank=rank, world=world)
+multi.comm_init(uid[0])
+rm = multi.SolverLinearStatics(m, merit_check=0)
+single = Solver(device=local)
+rs = single.SolverLinearStatics(m, node_index=rm.node_index, merit_check=0)
+
+du = np.linalg.norm(rm.U_full - rs.U_full) / np.linalg.norm(rs.U_full)
+ds = np.abs(rm.stress - rs.stress).max() / np.abs(rs.stress).max()
+ok = (du < 1e-9 and ds < 1e-7 and rm.cg.terminationtype == rs.cg.terminationtype == 1
+      and abs(rm.cg.iterationscount - rs.cg.iterationscount) <= 20)
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+print(f"rank {rank}/{world}: rows {multi.partition()}, its {rm.cg.iterationscount} vs {rs.cg.iterationscount}, "
+      f"|dU|/|U| = {du:.2e}, |dS|/|S| = {ds:.2e}, solve {rm.cg.solve_ms:.1f} ms vs {rs.cg.solve_ms:.1f} ms", flush=True)
+multi.close(); single.close()
+dist.destroy_process_group()
+sys.exit(0 if int(flag[0]) == 1 else 1)
