@@ -488,6 +488,104 @@ k_spmv_tile(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t *
     }
 }
 
+// ---- SpMV, bulk-copy tiles, three threads per scalar row ----------------------------------------
+// The tile kernel above is bound by the serial chain inside each thread (column -> x -> DFMA, 27
+// times; ptxas keeps only ~1 block of lookahead), so a stage is held for ~8000 cycles.  Here a tile
+// of 32 block rows (96 scalar rows = 3 full warps) is processed by 9 warps: warp (part, rw) owns
+// the blocks [part*nb/3, (part+1)*nb/3) of scalar rows 32*rw .. 32*rw+31.  Lanes of a warp still
+// read the same column slot of consecutive rows (few L1 lines per x gather); the three partial
+// sums of a row meet in shared memory after a group-wide named barrier, in a fixed order.
+constexpr int T3_ROWS = 32, T3_PARTS = 3, T3_GROUPS = 3;
+constexpr int T3_GW = 3 * T3_PARTS;                       // warps per group
+constexpr int T3_THREADS = 32 * (T3_GROUPS * T3_GW + 1);
+
+template <bool DOT>
+__global__ void __launch_bounds__(T3_THREADS, 1)
+k_spmv_tile3(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
+             const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, BulkLayout L,
+             double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar) {
+    if (st && st->done) return;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    __shared__ __align__(8) uint64_t s_full[T3_GROUPS], s_empty[T3_GROUPS];
+    __shared__ double s_part[T3_GROUPS][T3_PARTS][3 * T3_ROWS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t nchunks = (nrows + T3_ROWS - 1) / T3_ROWS;
+    const int64_t my_n = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0) {
+        for (int i = 0; i < T3_GROUPS; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], T3_GW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double dsum = 0.0;
+    if (warp == T3_GROUPS * T3_GW) {
+        if (lane == 0) {                                   // ---- producer ----
+            for (int64_t i = 0; i < my_n; i++) {
+                const int g = (int)(i % T3_GROUPS);
+                const int64_t k = i / T3_GROUPS;
+                if (k > 0) mbar_wait(&s_empty[g], (uint32_t)((k - 1) & 1));
+                const int64_t r0 = (blockIdx.x + i * (int64_t)gridDim.x) * T3_ROWS;
+                const int64_t r1 = (r0 + T3_ROWS < nrows) ? r0 + T3_ROWS : nrows;
+                unsigned char *base = s_raw + (size_t)g * L.stage_bytes;
+                const int64_t b0 = brow_ptr[r0], b1 = brow_ptr[r1];
+                const int64_t voff = 72 * b0, voff_al = voff & ~(int64_t)15;
+                const uint32_t vbytes = (uint32_t)(((voff - voff_al) + 72 * (b1 - b0) + 15) & ~(int64_t)15);
+                const int64_t coff = 4 * b0, coff_al = coff & ~(int64_t)15;
+                const uint32_t cbytes = (uint32_t)(((coff - coff_al) + 4 * (b1 - b0) + 15) & ~(int64_t)15);
+                const uint32_t rbytes = (uint32_t)((4 * (r1 - r0 + 1) + 15) & ~(int64_t)15);
+                mbar_expect_tx(&s_full[g], vbytes + cbytes + rbytes);
+                bulk_g2s(base + L.vals_off, (const unsigned char *)vals + voff_al, vbytes, &s_full[g]);
+                bulk_g2s(base + L.cols_off, (const unsigned char *)bcol + coff_al, cbytes, &s_full[g]);
+                bulk_g2s(base + L.rp_off, (const unsigned char *)(brow_ptr + r0), rbytes, &s_full[g]);
+            }
+        }
+    } else {
+        const int g = warp / T3_GW, wg = warp % T3_GW;     // ---- consumers ----
+        const int part = wg / 3, t = (wg % 3) * 32 + lane; // scalar row of the tile
+        const int br = t / 3, a = t - 3 * br;
+        const unsigned char *base = s_raw + (size_t)g * L.stage_bytes;
+        const int32_t *rp = reinterpret_cast<const int32_t *>(base + L.rp_off);
+        for (int64_t i = g, k = 0; i < my_n; i += T3_GROUPS, k++) {
+            mbar_wait(&s_full[g], (uint32_t)(k & 1));
+            const int64_t r0 = (blockIdx.x + i * (int64_t)gridDim.x) * T3_ROWS;
+            const int nr = (int)((nrows - r0) < T3_ROWS ? (nrows - r0) : T3_ROWS);
+            double acc = 0.0;
+            if (br < nr) {
+                const int b0 = rp[0];
+                const int sblk = rp[br] - b0, nb = rp[br + 1] - rp[br];
+                const int per = (nb + T3_PARTS - 1) / T3_PARTS;
+                const int c0 = part * per, c1 = (c0 + per < nb) ? c0 + per : nb;
+                const double *v = reinterpret_cast<const double *>(base + L.vals_off) + ((9 * (int64_t)b0) & 1) +
+                                  9 * sblk + a * 3 * nb;
+                const int32_t *cols = reinterpret_cast<const int32_t *>(base + L.cols_off) + (b0 & 3) + sblk;
+                double acc1 = 0.0, acc2 = 0.0;
+#pragma unroll 3
+                for (int c = c0; c < c1; c++) {
+                    const double *xp = x + 3 * (int64_t)cols[c];
+                    acc += v[3 * c] * xp[0];
+                    acc1 += v[3 * c + 1] * xp[1];
+                    acc2 += v[3 * c + 2] * xp[2];
+                }
+                acc = (acc + acc1) + acc2;
+            }
+            s_part[g][part][t] = acc;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(32 * T3_GW) : "memory");
+            if (part == 0 && br < nr) {
+                const double sum = (s_part[g][0][t] + s_part[g][1][t]) + s_part[g][2][t];
+                const int64_t dof = 3 * (r0 + br) + a;
+                y[dof] = sum;
+                if (DOT) dsum += sum * x[dof];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[g]);
+        }
+    }
+    if (DOT) {
+        double v[1] = {dsum};
+        grid_reduce<1>(v, partials, counter, st, slot, step, run_scalar);
+    }
+}
+
 // ---- vector kernels --------------------------------------------------------------------------
 // init: x = 0, r = b, p = z = b d^2; sums b.b and r.z
 __global__ void __launch_bounds__(VEC_THREADS)
@@ -593,10 +691,13 @@ static int vec_grid(const stan_handle *h, int64_t n) {
 static int spmv_variant() {
     static int v = -1;
     if (v < 0) {
-        // 0 = warp-per-row LDG kernel (default: 5.0 TB/s on the 10M beam, profiles/r01_spmv_variants.md),
-        // 1 = bulk-copy (TMA) pipeline (4.0 TB/s: consumer-latency bound, kept for further tuning)
+        // profiles/r01_spmv_variants.md, 10M beam:
+        // 4 = bulk-copy tiles, 3 threads per scalar row (default, 6.9 TB/s; falls back to 0 when a
+        //     32-row tile does not fit shared memory)
+        // 0 = warp-per-row LDG kernel (5.3 TB/s), 1 = bulk-copy ring + warp per row (5.0 TB/s),
+        // 2/3 = bulk-copy tiles, 1 thread per scalar row (5.5 / 4.8 TB/s)
         const char *e = getenv("STAN_SPMV");
-        v = e ? atoi(e) : 0;
+        v = e ? atoi(e) : 4;
     }
     return v;
 }
@@ -622,6 +723,19 @@ static int spmv_plan(const stan_handle *h, int64_t nrows, SpmvPlan *p) {
     p->variant = spmv_variant();
     p->L = bulk_layout(h);
     if (p->variant == 1 && p->L.stages < 2) p->variant = 0;   // rows too wide for the shared-memory ring
+    if (p->variant == 4) {                                    // 32-row tiles x 3 groups, 3 threads per scalar row
+        p->L = bulk_layout(h, T3_ROWS);
+        p->L.stages = T3_GROUPS;
+        p->smem = (size_t)T3_GROUPS * p->L.stage_bytes;
+        if (p->smem > 215 * 1024) p->variant = 0;
+        else {
+            STAN_CUDA(cudaFuncSetAttribute(k_spmv_tile3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+            STAN_CUDA(cudaFuncSetAttribute(k_spmv_tile3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+            const int64_t nchunks = (nrows + T3_ROWS - 1) / T3_ROWS;
+            p->grid = (int)(nchunks < h->sm_count ? (nchunks > 0 ? nchunks : 1) : h->sm_count);
+            return STAN_OK;
+        }
+    }
     if (p->variant == 2 || p->variant == 3) {                 // 2: 16-row tiles x 6 groups, 3: 32-row tiles x 3 groups
         const int tr = p->variant == 2 ? 16 : 32, groups = p->variant == 2 ? 6 : 3;
         p->L = bulk_layout(h, tr);
@@ -667,6 +781,15 @@ static void launch_spmv(const stan_handle *h, const SpmvPlan &p, bool dot, int64
 #define STAN_LAUNCH_TILE(D, R, G)                                                                                  \
     k_spmv_tile<D, R, G><<<p.grid, 32 * (G * ((3 * R + 31) / 32) + 1), p.smem, s>>>(                               \
         nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out, p.L, partials, counter, st, slot, step, run_scalar)
+    if (p.variant == 4) {
+        if (dot)
+            k_spmv_tile3<true><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out, p.L,
+                                                                  partials, counter, st, slot, step, run_scalar);
+        else
+            k_spmv_tile3<false><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out, p.L,
+                                                                   partials, counter, st, slot, step, run_scalar);
+        return;
+    }
     if (p.variant == 2) { if (dot) STAN_LAUNCH_TILE(true, 16, 6); else STAN_LAUNCH_TILE(false, 16, 6); return; }
     if (p.variant == 3) { if (dot) STAN_LAUNCH_TILE(true, 32, 3); else STAN_LAUNCH_TILE(false, 32, 3); return; }
 #undef STAN_LAUNCH_TILE
