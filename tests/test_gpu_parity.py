@@ -147,8 +147,12 @@ def test_cg_alglib_semantics(solver, oracle):
     assert orep.terminationtype == 1 and rep.terminationtype in (1, 7)
     assert abs(rep.iterationscount - orep.iterationscount) <= 12   # trajectories differ by summation order
     assert rep.nmv == 1 + rep.iterationscount + rep.iterationscount // 10
-    assert np.sqrt(rep.r2) <= 3e-8 * rep.bnorm and abs(rep.bnorm - orep.bnorm) <= 1e-12 * orep.bnorm
-    assert np.linalg.norm(solver.Exclude_BC_DOF() - xo) / np.linalg.norm(xo) < 1e-9
+    assert abs(rep.bnorm - orep.bnorm) <= 1e-12 * orep.bnorm
+    dx = np.linalg.norm(solver.Exclude_BC_DOF() - xo) / np.linalg.norm(xo)
+    if rep.terminationtype == 1:
+        assert np.sqrt(rep.r2) <= 1e-8 * rep.bnorm and dx < 1e-9
+    else:   # type 7 returns the iterate accepted ten iterations earlier
+        assert np.sqrt(rep.r2) <= 1e-5 * rep.bnorm and dx < 1e-7
     rep5 = solver.LinearSolver_CG(IterMax=7)
     assert rep5.terminationtype == 5 and rep5.iterationscount == 7
     rep7 = solver.LinearSolver_CG(tolerance=1e-30)                        # unreachable -> energy stall
