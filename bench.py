@@ -208,7 +208,8 @@ def run_ours(args):
     # ---- end to end through the C ABI with host buffers (H2D + D2H inside the timed region) ----
     h2d = m.xyz.nbytes + m.conn.nbytes + m.elem_type.nbytes + m.elem_mat.nbytes + ni.nbytes + m.spc_node.nbytes \
         + m.spc_val.nbytes + m.load_node.nbytes + m.load_val.nbytes + m.mat_E.nbytes + m.mat_nu.nbytes
-    d2h = m.n_dof * 8 + 2 * 48 * m.n_elem * 8
+    # every rank downloads the full displacement vector and the strain/stress of its element slice
+    d2h = world * m.n_dof * 8 + 2 * 48 * m.n_elem * 8
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):

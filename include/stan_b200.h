@@ -132,8 +132,10 @@ int stan_recover(stan_handle *h, stan_recovery_stats *stats);
 /* --- results: what Solver.cs:171-178,203-210 writes back into Node / Element --------------- */
 /* U_Full[nDOF] indexed by DOF (zeros at fixed DOFs). */
 int stan_get_displacements(stan_handle *h, double *u_full);
-/* Element.Strain[1] / Stress[1]: n_elem x 8 x 6 row-major each. */
+/* Element.Strain[1] / Stress[1]: 8 x 6 row-major per element, for the elements [first, last) of
+ * stan_get_element_range — all of ElemLib on one GPU, this rank's contiguous slice otherwise. */
 int stan_get_strain_stress(stan_handle *h, double *strain, double *stress);
+int stan_get_element_range(stan_handle *h, int64_t *first, int64_t *last);
 
 /* --- parity / inspection (SURVEY §8b "optional") ------------------------------------------- */
 int stan_get_dof_reduction(stan_handle *h, int32_t *ndof_reduction);          /* Solver.cs:121-132 */

@@ -282,7 +282,7 @@ int stan_get_displacements(stan_handle *h, double *u_full) {
 int stan_get_strain_stress(stan_handle *h, double *strain, double *stress) {
     STAN_TRY(check(h));
     if (!h->recovered) { set_error("stan_get_strain_stress before stan_recover"); return STAN_E_STATE; }
-    const size_t bytes = (size_t)48 * h->n_elem * sizeof(double);
+    const size_t bytes = (size_t)48 * (h->elem1 - h->elem0) * sizeof(double);
     if (strain) STAN_CUDA(cudaMemcpyAsync(strain, h->d_strain.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (stress) STAN_CUDA(cudaMemcpyAsync(stress, h->d_stress.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     STAN_CUDA(cudaStreamSynchronize(h->stream));
@@ -358,6 +358,14 @@ int stan_comm_unique_id(void *id128) { return comm_unique_id(id128); }
 int stan_comm_init(stan_handle *h, const void *id128) {
     STAN_TRY(check(h));
     return comm_init(h, id128);
+}
+
+int stan_get_element_range(stan_handle *h, int64_t *first, int64_t *last) {
+    if (!h) return STAN_E_ARG;
+    if (!h->recovered) { set_error("stan_get_element_range before stan_recover"); return STAN_E_STATE; }
+    if (first) *first = h->elem0;
+    if (last) *last = h->elem1;
+    return STAN_OK;
 }
 
 int stan_get_partition(stan_handle *h, int64_t *first_row, int64_t *last_row) {

@@ -114,6 +114,7 @@ struct stan_handle {
     // ---- partition ----
     int64_t row0 = 0, row1 = 0;         // owned BFS rows [row0, row1)
     int64_t n_halo = 0;                 // halo nodes appended after the owned rows in x vectors
+    int64_t elem0 = 0, elem1 = 0;       // elements whose strain/stress this rank recovers
 
     // ---- assembled system (local rows) ----
     stan::DevBuf<int32_t> d_inc_ptr;    // nloc+1: incidence CSR (row -> (elem<<3 | local node))

@@ -22,15 +22,15 @@ __constant__ double c_N[8][8];       // N[i][g], HEX8_ShapeFunctions(node i, 1/s
 constexpr int REC_THREADS = 128;     // 16 elements per CTA
 
 __global__ void __launch_bounds__(REC_THREADS)
-k_recover(int64_t n_elem, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
+k_recover(int64_t e_first, int64_t e_count, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
           const int32_t *__restrict__ node_index, const uint8_t *__restrict__ etype, const int32_t *__restrict__ emat,
           const double *__restrict__ lam_tab, const double *__restrict__ G_tab, const double *__restrict__ ufull,
           double *__restrict__ strain, double *__restrict__ stress, int32_t *err) {
     __shared__ double s_val[REC_THREADS / 8][8][12];
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t e = t >> 3;
+    const int64_t el = t >> 3, e = e_first + el;       // local / global element index
     const int g = (int)(t & 7), le = threadIdx.x >> 3;
-    const bool valid = e < n_elem;
+    const bool valid = el < e_count;
     int type = STAN_HEX8_G2;
     if (valid) {
         type = etype[e];
@@ -115,15 +115,13 @@ k_recover(int64_t n_elem, const int32_t *__restrict__ conn, const double *__rest
 #pragma unroll
         for (int c = 0; c < 12; c++) out[c] = s_val[le][0][c];
     }
-    double *so = strain + e * 48 + i * 6, *to = stress + e * 48 + i * 6;   // Update_StrainStress :257-267
+    double *so = strain + el * 48 + i * 6, *to = stress + el * 48 + i * 6;   // Update_StrainStress :257-267
 #pragma unroll
     for (int c = 0; c < 6; c += 2) {
         *reinterpret_cast<double2 *>(so + c) = make_double2(out[c], out[c + 1]);
         *reinterpret_cast<double2 *>(to + c) = make_double2(out[6 + c], out[6 + c + 1]);
     }
 }
-
-bool g_tables_ready = false;
 
 }  // namespace
 
@@ -148,12 +146,16 @@ int run_recovery(stan_handle *h, stan_recovery_stats *stats) {
     cudaStream_t s = h->stream;
     STAN_TRY(upload_recovery_tables());
     STAN_TRY(scatter_solution(h));
-    STAN_TRY(h->d_strain.alloc((size_t)48 * h->n_elem, s));
-    STAN_TRY(h->d_stress.alloc((size_t)48 * h->n_elem, s));
+    // every rank recovers (and later downloads) its own contiguous slice of ElemLib
+    h->elem0 = h->n_elem * (int64_t)h->rank / h->world;
+    h->elem1 = h->n_elem * (int64_t)(h->rank + 1) / h->world;
+    const int64_t ne = h->elem1 - h->elem0;
+    STAN_TRY(h->d_strain.alloc((size_t)48 * ne, s));
+    STAN_TRY(h->d_stress.alloc((size_t)48 * ne, s));
     STAN_CUDA(cudaMemsetAsync(h->d_err.p, 0, 4 * sizeof(int32_t), s));
     STAN_CUDA(cudaEventRecord(h->ev0, s));
-    k_recover<<<div_up(8 * h->n_elem, REC_THREADS), REC_THREADS, 0, s>>>(
-        h->n_elem, h->d_conn.p, h->d_xyz.p, h->d_node_index.p, h->d_etype.p, h->d_emat.p, h->d_lambda.p, h->d_G.p,
+    k_recover<<<div_up(8 * ne, REC_THREADS), REC_THREADS, 0, s>>>(
+        h->elem0, ne, h->d_conn.p, h->d_xyz.p, h->d_node_index.p, h->d_etype.p, h->d_emat.p, h->d_lambda.p, h->d_G.p,
         h->d_ufull.p, h->d_strain.p, h->d_stress.p, h->d_err.p);
     STAN_CUDA(cudaGetLastError());
     STAN_CUDA(cudaEventRecord(h->ev1, s));
@@ -166,7 +168,7 @@ int run_recovery(stan_handle *h, stan_recovery_stats *stats) {
     h->launches += 1;
     if (stats) {
         stats->recover_ms = ms;
-        stats->recover_bytes = h->n_elem * (32 + 768) + 24 * h->n_nodes * 2;
+        stats->recover_bytes = ne * (32 + 768) + 24 * h->n_nodes * 2 / h->world;
         stats->kernel_launches = 1;
     }
     h->recovered = true;

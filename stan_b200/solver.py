@@ -124,9 +124,16 @@ class Solver:
         native.check(self._lib.stan_get_solution_reduced(self._h, _p(u)))
         return u
 
+    def element_range(self):
+        a, b = C.c_int64(), C.c_int64()
+        native.check(self._lib.stan_get_element_range(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def strain_stress(self):
-        ne = self.model.n_elem
-        strain, stress = np.zeros((ne, 8, 6)), np.zeros((ne, 8, 6))
+        """Strain[1]/Stress[1] of this rank's element slice (all elements on one GPU)."""
+        e0, e1 = self.element_range()
+        ne = e1 - e0
+        strain, stress = np.empty((ne, 8, 6)), np.empty((ne, 8, 6))
         native.check(self._lib.stan_get_strain_stress(self._h, _p(strain), _p(stress)))
         return strain, stress
 
