@@ -65,5 +65,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_SRC = os.path.join(HERE, "host")
+HOST_BIN = os.path.join(OUT_DIR, "stan_solver")
+CXX = "/usr/bin/g++"   # the image's $CXX wrapper lacks some specs; the system g++ is complete
+
+
+def build_host(force: bool = False) -> str:
+    """Native solver host (STdb codec, BDF import, console driver) linked against libstan_b200.so."""
+    lib = build(force=False)
+    srcs = [os.path.join(HOST_SRC, f) for f in ("stan_solver.cpp", "stdb.cpp", "bdf.cpp")]
+    deps = srcs + [os.path.join(HOST_SRC, f) for f in os.listdir(HOST_SRC) if f.endswith(".hpp")] + [lib]
+    if force or _stale(HOST_BIN, deps):
+        cmd = [CXX, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", HOST_BIN] + srcs + \
+              ["-L" + OUT_DIR, "-lstan_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + "/usr/local/cuda/lib64"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            raise RuntimeError(f"host build failed:\n{r.stdout}\n{r.stderr}")
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

@@ -1,0 +1,102 @@
+"""Native host pieces that need no GPU: STdb codec (two independent implementations against each
+other and against hand-assembled wire bytes) and the Nastran import (Database.ReadNastranMesh)."""
+import json
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from stan_b200 import mesh, stdb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host():
+    from stan_b200 import build
+    return build.build_host()
+
+
+def _run(host, *args):
+    r = subprocess.run([host, *args], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def test_wire_known_answer():
+    # Database{NodeLib: {7: Node{ID=7, X=1.5, DOF=[0,1,2]}}, nDOF=3} assembled by hand from the protobuf spec
+    node = b"\x08\x07" + b"\x11" + struct.pack("<d", 1.5) + b"\x30\x00\x30\x01\x30\x02"
+    entry = b"\x08\x07" + b"\x12" + bytes([len(node)]) + node
+    golden = b"\x0a" + bytes([len(entry)]) + entry + b"\x28\x03"
+    db = stdb.Database(nodes=[stdb.Node(id=7, x=1.5, dof=[0, 1, 2])], ndof=3)
+    assert stdb.encode(db) == golden
+    back = stdb.decode(golden)
+    assert back.nodes[0].id == 7 and back.nodes[0].x == 1.5 and back.nodes[0].y == 0.0 and back.nodes[0].dof == [0, 1, 2]
+    assert back.ndof == 3
+    # negative int32 is a 10-byte varint; packed and unpacked repeated scalars decode alike
+    neg = stdb.decode(stdb.encode(stdb.Database(nodes=[stdb.Node(id=-5, elist=[-1, 3])])))
+    assert neg.nodes[0].id == -5 and neg.nodes[0].elist == [-1, 3]
+    packed_node = b"\x08\x07" + b"\x32\x03\x00\x01\x02" + b"\x3a\x10" + struct.pack("<dd", 0.0, 2.5)
+    e2 = b"\x08\x07\x12" + bytes([len(packed_node)]) + packed_node
+    p = stdb.decode(b"\x0a" + bytes([len(e2)]) + e2)
+    assert p.nodes[0].dof == [0, 1, 2] and p.nodes[0].dispx == [0.0, 2.5]
+
+
+def test_python_and_native_codec_agree(host, tmp_path):
+    m = mesh.beam(3, 2, 4, jitter=True, n_parts=2, tolerance=1e-7, max_iter=123)
+    db = stdb.from_model(m)
+    db.info_raw = b"\x0a\x06\x08\x01\x12\x02\x08\x03"            # opaque Information payload must survive
+    db.elems[0].strain = [stdb.MatrixST([0.0] * 48, 8, 6), stdb.MatrixST(list(np.arange(48.0) - 7), 8, 6)]
+    raw = stdb.encode(db)
+    a, b = tmp_path / "a.STdb", tmp_path / "b.STdb"
+    a.write_bytes(raw)
+    _run(host, "--roundtrip", str(a), str(b))
+    assert b.read_bytes() == raw                                 # byte-identical re-serialisation
+    d = json.loads(_run(host, "--dump", str(a)))
+    assert d["nodes"] == m.n_nodes and d["elements"] == m.n_elem and d["materials"] == 2 and d["bcs"] == 2
+    assert d["ndof"] == m.n_dof and d["analysis"] == "Linear_Statics" and d["linsolver"] == "CG"
+    assert d["tolerance"] == 1e-7 and d["itermax"] == 123 and d["result_stepno"] == 0
+    back = stdb.decode(raw)
+    assert [n.id for n in back.nodes] == list(range(1, m.n_nodes + 1))
+    assert back.elems[5].nlist == [int(v) + 1 for v in m.conn[5]] and back.elems[5].matid == int(m.elem_mat[5]) + 1
+    assert back.bcs[0][1].type == "SPC" and back.bcs[1][1].nodal[0][1].M == list(m.load_val[0])
+    assert back.info_raw == db.info_raw and back.elems[0].strain[1].array()[7, 5] == 40.0
+
+
+def test_truncated_file_is_an_error(host, tmp_path):
+    raw = stdb.encode(stdb.from_model(mesh.beam(1, 1, 1)))
+    p = tmp_path / "t.STdb"
+    p.write_bytes(raw[: len(raw) // 2])
+    r = subprocess.run([host, "--dump", str(p)], capture_output=True, text=True)
+    assert r.returncode != 0 and "malformed" in r.stderr.lower() or "truncated" in r.stderr.lower()
+
+
+def test_bdf_import_readme_excerpt(host, tmp_path):
+    out = tmp_path / "m.STdb"
+    rep = json.loads(_run(host, "--import-bdf", os.path.join(ROOT, "tests", "golden", "readme_excerpt.bdf"), str(out)))
+    assert rep == {"nodes": 3, "elements": 3, "import_errors": 0}
+    db = stdb.decode(out.read_bytes())
+    assert [(n.id, n.x, n.y, n.z) for n in db.nodes] == [(1, 0.0, 15.0, 0.0), (2, -7.11e-15, 5.0, 0.0), (3, 0.0, -5.0, 0.0)]
+    assert db.elems[0].nlist == [573, 570, 571, 572, 1236, 1237, 1238, 1239] and db.elems[0].pid == 1
+    assert db.elems[2].nlist == [576, 573, 572, 574, 1242, 1236, 1239, 1243]
+    assert all(e.type == "HEX8_G2" and e.matid == 0 for e in db.elems)       # Element.cs:59, :64
+    assert db.ndof == 9 and db.analysis.linsolver == "CG" and db.analysis.tolerance == 1e-6
+
+
+def test_bdf_import_of_generated_mesh(host, tmp_path):
+    m = mesh.beam(3, 2, 2)
+    bdf, out = tmp_path / "g.bdf", tmp_path / "g.STdb"
+    mesh.write_bdf(m, str(bdf))
+    rep = json.loads(_run(host, "--import-bdf", str(bdf), str(out)))
+    assert rep["nodes"] == m.n_nodes and rep["elements"] == m.n_elem and rep["import_errors"] == 0
+    db = stdb.decode(out.read_bytes())
+    np.testing.assert_array_equal(np.array([[n.x, n.y, n.z] for n in db.nodes]), m.xyz)
+    np.testing.assert_array_equal(np.array([e.nlist for e in db.elems]), m.conn + 1)
+    # quirks of the reference parser: '+' exponents are not patched (node dropped), duplicate ids are dropped
+    bad = tmp_path / "bad.bdf"
+    bad.write_text("GRID           1             0.0     1.0     2.0\nGRID           1             9.0     9.0     9.0\n"
+                   "GRID           2         7.11+15     5.0     0.0\nCTETRA         9       1       1       2       3       4\n")
+    rep = json.loads(_run(host, "--import-bdf", str(bad), str(out)))
+    assert rep == {"nodes": 1, "elements": 0, "import_errors": 2}
