@@ -137,6 +137,13 @@ int stan_get_displacements(stan_handle *h, double *u_full);
 int stan_get_strain_stress(stan_handle *h, double *strain, double *stress);
 int stan_get_element_range(stan_handle *h, int64_t *first, int64_t *last);
 
+/* --- post-processing: Part.Load_Scalar, Part.cs:231-528 ------------------ */
+/* 24 scalar fields (displacement x/y/z/total, stress xx..xz, P1..P3, von Mises, strain xx..xz,
+ * P1..P3, effective strain) as float32: cell = n_elem x 24 x {max, average, min} over the element's
+ * nodes, point = n_nodes x 24 averaged over the elements containing the node (NodeLib order). */
+int stan_postprocess(stan_handle *h, double *device_ms);
+int stan_get_scalars(stan_handle *h, float *cell, float *point);
+
 /* --- parity / inspection (SURVEY §8b "optional") ------------------------------------------- */
 int stan_get_dof_reduction(stan_handle *h, int32_t *ndof_reduction);          /* Solver.cs:121-132 */
 int stan_get_rhs(stan_handle *h, double *F_reduced);                          /* Solver.cs:136-152 */

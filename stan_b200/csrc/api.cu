@@ -33,7 +33,7 @@ static int upload_dof_map(stan_handle *h, const int32_t *node_index) {
                               cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaStreamSynchronize(s));
     h->have_dof = true;
-    h->assembled = h->solved = h->recovered = false;
+    h->assembled = h->solved = h->recovered = h->postprocessed = false;
     return STAN_OK;
 }
 
@@ -88,6 +88,7 @@ int stan_destroy(stan_handle *h) {
     h->d_b.release(s); h->d_d2.release(s); h->d_err.release(s); h->d_x.release(s); h->d_xalt.release(s);
     h->d_r.release(s); h->d_p.release(s); h->d_mv.release(s); h->d_partials.release(s); h->d_state.release(s);
     h->d_counter.release(s); h->d_ufull.release(s); h->d_strain.release(s); h->d_stress.release(s);
+    h->d_cell.release(s); h->d_point.release(s);
     cudaStreamSynchronize(s);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
     for (int i = 0; i < 8; i++) if (h->user_ev[i]) cudaEventDestroy(h->user_ev[i]);
@@ -127,7 +128,7 @@ int stan_set_mesh(stan_handle *h, int64_t n_nodes, const double *xyz, int64_t n_
     for (int64_t e = 0; e < n_elem; e++) { if (elem_mat[e] < 0) { set_error("negative material index"); return STAN_E_ARG; } mmax = std::max(mmax, elem_mat[e]); }
     h->n_mat = std::max(h->n_mat, 0);
     h->have_mesh = true;
-    h->have_dof = h->assembled = h->solved = h->recovered = false;
+    h->have_dof = h->assembled = h->solved = h->recovered = h->postprocessed = false;
     h->h_spc_node.clear(); h->h_spc_val.clear(); h->h_load_node.clear(); h->h_load_val.clear();
     (void)mmax;
     return STAN_OK;
@@ -150,7 +151,7 @@ int stan_set_materials(stan_handle *h, int32_t n_mat, const double *E, const dou
     STAN_CUDA(cudaStreamSynchronize(s));
     h->n_mat = n_mat;
     h->have_mat = true;
-    h->assembled = h->solved = h->recovered = false;
+    h->assembled = h->solved = h->recovered = h->postprocessed = false;
     return STAN_OK;
 }
 
@@ -184,7 +185,7 @@ int stan_set_spc(stan_handle *h, int64_t n, const int32_t *node, const double *v
         if (node[i] < 0 || node[i] >= h->n_nodes) { set_error("SPC entry %lld: node %d not in the mesh", (long long)i, node[i]); return STAN_E_ARG; }
     h->h_spc_node.assign(node, node + n);
     h->h_spc_val.assign(val3, val3 + 3 * n);
-    h->assembled = h->solved = h->recovered = false;
+    h->assembled = h->solved = h->recovered = h->postprocessed = false;
     return STAN_OK;
 }
 
@@ -196,7 +197,7 @@ int stan_set_loads(stan_handle *h, int64_t n, const int32_t *node, const double 
         if (node[i] < 0 || node[i] >= h->n_nodes) { set_error("load entry %lld: node %d not in the mesh", (long long)i, node[i]); return STAN_E_ARG; }
     h->h_load_node.assign(node, node + n);
     h->h_load_val.assign(fxyz, fxyz + 3 * n);
-    h->assembled = h->solved = h->recovered = false;
+    h->assembled = h->solved = h->recovered = h->postprocessed = false;
     return STAN_OK;
 }
 
@@ -207,7 +208,7 @@ int stan_assemble(stan_handle *h, stan_assembly_stats *stats) {
     }
     cudaStream_t s = h->stream;
     const int64_t launches0 = h->launches;
-    h->assembled = h->solved = h->recovered = false;
+    h->assembled = h->solved = h->recovered = h->postprocessed = false;
     partition_rows(h);
     STAN_CUDA(cudaEventRecord(h->ev2, s));
     STAN_TRY(build_system_pattern(h));
@@ -259,7 +260,7 @@ int stan_solve_cg(stan_handle *h, const stan_cg_options *opts, stan_cg_report *r
         return STAN_E_ARG;
     }
     memset(report, 0, sizeof *report);
-    h->recovered = false;
+    h->recovered = h->postprocessed = false;
     return solve_cg(h, opts, report);
 }
 
@@ -285,6 +286,21 @@ int stan_get_strain_stress(stan_handle *h, double *strain, double *stress) {
     const size_t bytes = (size_t)48 * (h->elem1 - h->elem0) * sizeof(double);
     if (strain) STAN_CUDA(cudaMemcpyAsync(strain, h->d_strain.p, bytes, cudaMemcpyDeviceToHost, h->stream));
     if (stress) STAN_CUDA(cudaMemcpyAsync(stress, h->d_stress.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    STAN_CUDA(cudaStreamSynchronize(h->stream));
+    return STAN_OK;
+}
+
+int stan_postprocess(stan_handle *h, double *ms) {
+    STAN_TRY(check(h));
+    if (!h->recovered) { set_error("stan_postprocess before stan_recover"); return STAN_E_STATE; }
+    return run_postprocess(h, ms);
+}
+
+int stan_get_scalars(stan_handle *h, float *cell, float *point) {
+    STAN_TRY(check(h));
+    if (!h->postprocessed || !h->recovered) { set_error("stan_get_scalars before stan_postprocess"); return STAN_E_STATE; }
+    if (cell) STAN_CUDA(cudaMemcpyAsync(cell, h->d_cell.p, (size_t)h->n_elem * 72 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (point) STAN_CUDA(cudaMemcpyAsync(point, h->d_point.p, (size_t)h->n_nodes * 24 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     STAN_CUDA(cudaStreamSynchronize(h->stream));
     return STAN_OK;
 }

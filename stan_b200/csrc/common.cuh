@@ -142,6 +142,8 @@ struct stan_handle {
     // ---- results ----
     stan::DevBuf<double> d_ufull;       // 3*n_nodes in DOF order (all ranks after the gather)
     stan::DevBuf<double> d_strain, d_stress;  // 48*n_elem
+    stan::DevBuf<float> d_cell, d_point;      // post-processing scalars: [elem][24][3], [node][24]
+    bool postprocessed = false;
 
     stan::Comm *comm = nullptr;
     int64_t launches = 0;
@@ -173,6 +175,9 @@ int scatter_solution(stan_handle *h);
 
 // recovery.cu
 int run_recovery(stan_handle *h, stan_recovery_stats *st);
+
+// postprocess.cu
+int run_postprocess(stan_handle *h, double *ms);
 
 // comm.cu
 int comm_unique_id(void *id128);

@@ -67,6 +67,8 @@ SYMBOLS = {
     "stan_get_displacements": (C.c_int, [_P, _P]),
     "stan_get_strain_stress": (C.c_int, [_P, _P, _P]),
     "stan_get_element_range": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
+    "stan_postprocess": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "stan_get_scalars": (C.c_int, [_P, _P, _P]),
     "stan_get_dof_reduction": (C.c_int, [_P, _P]),
     "stan_get_rhs": (C.c_int, [_P, _P]),
     "stan_get_solution_reduced": (C.c_int, [_P, _P]),

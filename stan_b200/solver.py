@@ -137,6 +137,15 @@ class Solver:
         native.check(self._lib.stan_get_strain_stress(self._h, _p(strain), _p(stress)))
         return strain, stress
 
+    def Load_Scalar(self):
+        """Part.Load_Scalar (Part.cs:231-528): returns (cell (n_elem,24,3) max/average/min, point (n_nodes,24), ms)."""
+        ms = C.c_double()
+        native.check(self._lib.stan_postprocess(self._h, C.byref(ms)))
+        cell = np.empty((self.model.n_elem, 24, 3), dtype=np.float32)
+        point = np.empty((self.model.n_nodes, 24), dtype=np.float32)
+        native.check(self._lib.stan_get_scalars(self._h, _p(cell), _p(point)))
+        return cell, point, ms.value
+
     def nDOF_reduction(self) -> np.ndarray:
         red = np.zeros(self.model.n_dof, dtype=np.int32)
         native.check(self._lib.stan_get_dof_reduction(self._h, _p(red)))
