@@ -276,8 +276,8 @@ int run_assembly(stan_handle *h) {
 
 int element_stiffness(stan_handle *h, int64_t first, int64_t count, double *ke_host) {
     cudaStream_t s = h->stream;
-    STAN_TRY(h->d_err.alloc(4, s));
-    STAN_CUDA(cudaMemsetAsync(h->d_err.p, 0, 4 * sizeof(int32_t), s));
+    STAN_TRY(h->d_err.alloc(8, s));
+    STAN_CUDA(cudaMemsetAsync(h->d_err.p, 0, 8 * sizeof(int32_t), s));
     DevBuf<double> ke;
     STAN_TRY(ke.alloc((size_t)count * 576, s));
     k_element_ke<<<div_up(8 * count, 128), 128, 0, s>>>(first, count, h->d_conn.p, h->d_xyz.p, h->d_etype.p,

@@ -83,6 +83,41 @@ __device__ void scalar_step(CgState *st, int step) {
     }
 }
 
+// Multi-GPU, peer-memory mode: the thread that holds this rank's partial sums writes them into every
+// peer's window over NVLink, raises a sequence flag, waits for the peers' flags and adds the W
+// contributions in rank order — every rank obtains bitwise identical sums, so all ranks take the
+// same branches.  Slots are double-buffered by sequence parity; a rank cannot be two reductions ahead
+// of a peer because each reduction needs that peer's contribution.
+__device__ void cross_rank_sum(CgState *st, int cnt) {
+    CommDev *cd = st->comm;
+    const int W = cd->world, me = cd->rank;
+    const unsigned long long seq = ++st->red_seq;
+    const int par = (int)(seq & 1);
+    for (int r = 0; r < W; r++) {
+        if (r == me) continue;
+        for (int i = 0; i < cnt; i++) cd->ctrl[r]->red[par][me][i] = st->partial[i];
+    }
+    __threadfence_system();
+    for (int r = 0; r < W; r++)
+        if (r != me) *(volatile unsigned long long *)&cd->ctrl[r]->rflag[par][me] = seq;
+    double sum[4] = {0.0, 0.0, 0.0, 0.0};
+    P2PCtrl *mine = cd->ctrl[me];
+    for (int r = 0; r < W; r++) {
+        if (r == me) {
+            for (int i = 0; i < cnt; i++) sum[i] += st->partial[i];
+            continue;
+        }
+        volatile unsigned long long *f = &mine->rflag[par][r];
+        const long long t0 = clock64();
+        while (*f < seq) {
+            if (clock64() - t0 > 8000000000LL) { atomicOr(cd->err + 4, 1); st->type = -4; st->done = 1; return; }
+        }
+        __threadfence_system();
+        for (int i = 0; i < cnt; i++) sum[i] += __ldcg(&mine->red[par][r][i]);
+    }
+    for (int i = 0; i < cnt; i++) st->partial[i] = sum[i];
+}
+
 __global__ void k_scalar(CgState *st, int step) {
     if (st->done) return;
     scalar_step(st, step);
@@ -144,7 +179,10 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partials, u
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             if (lane == 0) st->partial[slot0 + i] = x;
         }
-        if (lane == 0 && run_scalar && step != SC_NONE) scalar_step(st, step);
+        if (lane == 0 && run_scalar && step != SC_NONE) {
+            if (st->comm) cross_rank_sum(st, step == SC_AFTER_REFRESH ? 4 : (step == SC_AFTER_SPMV ? 1 : 2));
+            if (!st->done) scalar_step(st, step);
+        }
     }
 }
 
@@ -815,7 +853,8 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     cudaStream_t s = h->stream;
     const int64_t nloc = h->row1 - h->row0, n = 3 * nloc, nx = 3 * (nloc + h->n_halo);
     const bool multi = h->world > 1;
-    const bool single = !multi;
+    const bool p2p = multi && comm_p2p_active(h);
+    const bool single = !multi || p2p;      // reductions finish inside the producing kernel
     double epsf = o->epsf;
     if (epsf == 0.0 && o->maxits == 0) epsf = 1.0e-6;      // lincgsetcond note (SolverFunctions.cs:292-293)
     const int rupd = o->its_before_rupdate;
@@ -842,6 +881,8 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     init.epsf_bnorm = epsf;
     init.maxits = o->maxits; init.rupdate = rupd; init.merit_check = o->merit_check; init.counter_off = off;
     init.restart = restart;
+    init.comm = p2p ? comm_dev(h) : nullptr;
+    init.red_seq = h->red_seq;              // flags in the peer windows persist across solves
     CgState *hst = nullptr;
     STAN_CUDA(cudaMallocHost((void **)&hst, sizeof(CgState)));
     *hst = init;
@@ -856,7 +897,7 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
 
     STAN_CUDA(cudaEventRecord(h->ev0, s));
     auto reduce_tail = [&](int step) -> int {              // multi-GPU: all-reduce the sums, then one scalar thread
-        if (single) return STAN_OK;
+        if (single) return STAN_OK;   // one GPU, or peer-memory mode: cross_rank_sum ran in the kernel
         const int cnt = step == SC_AFTER_SPMV ? 1 : (step == SC_AFTER_REFRESH ? 4 : 2);
         STAN_TRY(comm_allreduce_sum(h, (double *)((char *)st + offsetof(CgState, partial)), cnt, s));
         k_scalar<<<1, 1, 0, s>>>(st, step);
@@ -864,7 +905,7 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
         return STAN_OK;
     };
     auto spmv = [&](double *in, int slot, int step) -> int {
-        if (multi) STAN_TRY(comm_halo_exchange(h, in, s));
+        if (multi) STAN_TRY(comm_halo_exchange(h, in, s, st));
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (timek) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
         launch_spmv(h, plan, true, nloc, in, h->d_mv.p, h->d_partials.p, h->d_counter.p + 2, st, slot, step, single, s);
@@ -925,6 +966,7 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     }
     // accepted iterate: d_x unless an odd number of refreshes were accepted
     h->x_in_alt = hst->x_in_alt != 0;
+    h->red_seq = hst->red_seq;
     rep->terminationtype = hst->type;
     rep->iterationscount = hst->k;
     rep->nmv = hst->nmv;
@@ -938,6 +980,11 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     rep->kernel_launches = launches;
     h->launches += launches;
     cudaFreeHost(hst);
+    if (p2p) {                                             // a peer never raised its flag (spin timed out)
+        int32_t herr[8] = {0};
+        STAN_CUDA(cudaMemcpy(herr, h->d_err.p, sizeof herr, cudaMemcpyDeviceToHost));
+        if (herr[4]) { set_error("peer-memory exchange timed out: a rank stopped participating"); return STAN_E_COMM; }
+    }
     h->solved = true;
     return STAN_OK;
 }

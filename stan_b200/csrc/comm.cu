@@ -63,6 +63,14 @@ static int load_nccl() {
 
 struct Comm {
     nccl_comm comm = nullptr;
+    // ---- peer-memory path ----
+    bool p2p = false, p2p_failed = false;
+    void *window = nullptr;                // this rank's cudaMalloc'ed window (P2PCtrl + landing zones)
+    size_t window_bytes = 0;
+    void *peer_window[P2P_MAX_RANKS] = {};   // IPC mappings of the other ranks' windows
+    DevBuf<CommDev> d_dev;
+    DevBuf<unsigned int> d_ticket;
+    unsigned long long halo_seq = 0;       // monotonic across solves
     std::vector<int64_t> bound;            // world+1 row bounds
     std::vector<int64_t> recv_off, recv_cnt;   // per peer: segment of the halo region (nodes)
     std::vector<int64_t> send_off, send_cnt;   // per peer: segment of the send list (nodes)
@@ -89,8 +97,24 @@ int comm_init(stan_handle *h, const void *id128) {
     return STAN_OK;
 }
 
+static void p2p_release(stan_handle *h) {
+    Comm *c = h->comm;
+    if (!c) return;
+    for (int r = 0; r < P2P_MAX_RANKS; r++)
+        if (c->peer_window[r]) { cudaIpcCloseMemHandle(c->peer_window[r]); c->peer_window[r] = nullptr; }
+    if (c->window) { cudaFree(c->window); c->window = nullptr; }
+    c->p2p = false;
+}
+
+bool comm_p2p_active(const stan_handle *h) { return h->comm && h->comm->p2p; }
+CommDev *comm_dev(const stan_handle *h) { return comm_p2p_active(h) ? h->comm->d_dev.p : nullptr; }
+
 void comm_destroy(stan_handle *h) {
     if (!h->comm) return;
+    cudaStreamSynchronize(h->stream);
+    p2p_release(h);
+    h->comm->d_dev.release(h->stream);
+    h->comm->d_ticket.release(h->stream);
     if (h->comm->comm) g_nccl.CommDestroy(h->comm->comm);
     h->comm->d_send_rows.release(h->stream);
     h->comm->d_sendbuf.release(h->stream);
@@ -140,6 +164,53 @@ __global__ void k_peer_mask(int64_t nloc, const int32_t *__restrict__ brow_ptr, 
     mask[p] = m;
 }
 
+// Halo push: my boundary rows go straight into the landing zones of the ranks that read them.
+// The last CTA to finish raises the arrival flags (sequence number) after a system-scope fence.
+__global__ void __launch_bounds__(256)
+k_halo_push(const CommDev *__restrict__ cd, const int32_t *__restrict__ rows, const double *__restrict__ vec,
+            unsigned long long seq, unsigned int *ticket, const CgState *st) {
+    if (st && st->done) return;
+    const int W = cd->world, me = cd->rank, par = (int)(seq & 1);
+    const long long n3 = 3 * cd->send_off[W];
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n3; t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t / 3;
+        int peer = 0;
+        while (i >= cd->send_off[peer + 1]) peer++;
+        double *dst = cd->rbuf[peer] + par * cd->rbuf_stride[peer] + 3 * (cd->land_off[peer] + (i - cd->send_off[peer])) + (t - 3 * i);
+        *dst = vec[3 * (long long)rows[i] + (t - 3 * i)];
+    }
+    __threadfence_system();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+    __syncthreads();
+    if (last && threadIdx.x < W && threadIdx.x != me && cd->send_off[threadIdx.x + 1] > cd->send_off[threadIdx.x]) {
+        __threadfence_system();
+        *(volatile unsigned long long *)&cd->ctrl[threadIdx.x]->hflag[par][me] = seq;
+    }
+}
+
+// Halo wait: spin until every source rank has raised its flag for this exchange, then move the
+// landing zone (read through L2: the lines were written by a peer) behind the owned entries of vec.
+__global__ void __launch_bounds__(256)
+k_halo_wait(const CommDev *__restrict__ cd, double *__restrict__ vec, long long nloc3, long long nhalo3,
+            unsigned long long seq, CgState *st) {
+    if (st && st->done) return;
+    const int W = cd->world, me = cd->rank, par = (int)(seq & 1);
+    if (threadIdx.x < W && threadIdx.x != me && cd->recv_cnt[threadIdx.x] > 0) {
+        volatile unsigned long long *f = &cd->ctrl[me]->hflag[par][threadIdx.x];
+        const long long t0 = clock64();
+        while (*f < seq) {
+            if (clock64() - t0 > 8000000000LL) { atomicOr(cd->err + 4, 1); break; }   // ~4 s: a peer died
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const double *src = cd->rbuf[me] + par * cd->rbuf_stride[me];
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nhalo3; t += (long long)gridDim.x * blockDim.x)
+        vec[nloc3 + t] = __ldcg(src + t);
+}
+
 __global__ void k_pack(int64_t n_send, const int32_t *__restrict__ rows, const double *__restrict__ vec,
                        double *__restrict__ buf) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -152,6 +223,103 @@ __global__ void k_pack(int64_t n_send, const int32_t *__restrict__ rows, const d
 void partition_rows(stan_handle *h) {
     h->row0 = h->n_nodes * (int64_t)h->rank / h->world;
     h->row1 = h->n_nodes * (int64_t)(h->rank + 1) / h->world;
+}
+
+// Peer-memory set-up: allocate this rank's window, swap IPC handles and landing offsets with an
+// NCCL all-gather (set-up only), map every peer window.  Falls back to the NCCL path when IPC is
+// unavailable or STAN_COMM=nccl.
+static int p2p_setup(stan_handle *h) {
+    Comm *c = h->comm;
+    cudaStream_t s = h->stream;
+    const int W = h->world, me = h->rank;
+    const char *mode = getenv("STAN_COMM");
+    if ((mode && !strcmp(mode, "nccl")) || W > P2P_MAX_RANKS || c->p2p_failed) return STAN_OK;
+
+    // phase 1: sizes and landing offsets (also a barrier: every rank has left its previous solve)
+    struct Hello { long long n_halo, need, cap; long long recv_off[P2P_MAX_RANKS]; };
+    struct Hello2 { cudaIpcMemHandle_t handle; int ok, pad; };
+    const size_t ctrl_bytes = (sizeof(P2PCtrl) + 255) & ~(size_t)255;
+    Hello mine;
+    memset(&mine, 0, sizeof mine);
+    mine.n_halo = h->n_halo;
+    mine.need = (long long)(ctrl_bytes + 2 * (size_t)(3 * std::max<int64_t>(h->n_halo, 1)) * sizeof(double));
+    mine.cap = c->window ? (long long)c->window_bytes : 0;
+    for (int r = 0; r < W; r++) mine.recv_off[r] = c->recv_off[r];
+    std::vector<Hello> all(W);
+    {
+        DevBuf<Hello> dmine, dall;
+        STAN_TRY(dmine.alloc(1, s)); STAN_TRY(dall.alloc(W, s));
+        STAN_CUDA(cudaMemcpyAsync(dmine.p, &mine, sizeof mine, cudaMemcpyHostToDevice, s));
+        STAN_NCCL(g_nccl.AllGather(dmine.p, dall.p, sizeof(Hello), 0 /* ncclInt8 */, c->comm, s));
+        STAN_CUDA(cudaMemcpyAsync(all.data(), dall.p, W * sizeof(Hello), cudaMemcpyDeviceToHost, s));
+        STAN_CUDA(cudaStreamSynchronize(s));
+        dmine.release(s); dall.release(s);
+    }
+    bool any_grow = false;
+    for (int r = 0; r < W; r++) any_grow = any_grow || all[r].need > all[r].cap;
+
+    // phase 2 (only when some window must grow): new allocations, new IPC handles, new mappings
+    if (any_grow) {
+        Hello2 m2;
+        memset(&m2, 0, sizeof m2);
+        m2.ok = 1;
+        if (all[me].need > all[me].cap) {
+            if (c->window) { cudaFree(c->window); c->window = nullptr; }
+            c->window_bytes = std::max<size_t>((size_t)all[me].need * 2, (size_t)1 << 20);
+            m2.ok = cudaMalloc(&c->window, c->window_bytes) == cudaSuccess;
+            if (m2.ok) cudaMemset(c->window, 0, c->window_bytes);
+        }
+        if (m2.ok) m2.ok = cudaIpcGetMemHandle(&m2.handle, c->window) == cudaSuccess;
+        cudaGetLastError();
+        std::vector<Hello2> all2(W);
+        DevBuf<Hello2> dmine, dall;
+        STAN_TRY(dmine.alloc(1, s)); STAN_TRY(dall.alloc(W, s));
+        STAN_CUDA(cudaMemcpyAsync(dmine.p, &m2, sizeof m2, cudaMemcpyHostToDevice, s));
+        STAN_NCCL(g_nccl.AllGather(dmine.p, dall.p, sizeof(Hello2), 0, c->comm, s));
+        STAN_CUDA(cudaMemcpyAsync(all2.data(), dall.p, W * sizeof(Hello2), cudaMemcpyDeviceToHost, s));
+        STAN_CUDA(cudaStreamSynchronize(s));
+        dmine.release(s); dall.release(s);
+        bool ok = true;
+        for (int r = 0; r < W; r++) ok = ok && all2[r].ok;
+        for (int r = 0; r < W && ok; r++) {
+            if (r == me || !(all[r].need > all[r].cap)) continue;       // unchanged windows keep their mapping
+            if (c->peer_window[r]) { cudaIpcCloseMemHandle(c->peer_window[r]); c->peer_window[r] = nullptr; }
+            if (cudaIpcOpenMemHandle(&c->peer_window[r], all2[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+        }
+        cudaGetLastError();
+        // every rank must take the same path: agree on success
+        double flag = ok ? 0.0 : 1.0;
+        DevBuf<double> dflag;
+        STAN_TRY(dflag.alloc(1, s));
+        STAN_CUDA(cudaMemcpyAsync(dflag.p, &flag, sizeof flag, cudaMemcpyHostToDevice, s));
+        STAN_NCCL(g_nccl.AllReduce(dflag.p, dflag.p, 1, NCCL_F64, NCCL_SUM, c->comm, s));
+        STAN_CUDA(cudaMemcpyAsync(&flag, dflag.p, sizeof flag, cudaMemcpyDeviceToHost, s));
+        STAN_CUDA(cudaStreamSynchronize(s));
+        dflag.release(s);
+        if (flag != 0.0) { p2p_release(h); c->p2p_failed = true; return STAN_OK; }   // NCCL path on every rank
+    }
+    CommDev dev;
+    memset(&dev, 0, sizeof dev);
+    dev.rank = me; dev.world = W; dev.err = h->d_err.p;
+    for (int r = 0; r < W; r++) {
+        void *base = r == me ? c->window : c->peer_window[r];
+        dev.ctrl[r] = (P2PCtrl *)base;
+        dev.rbuf[r] = (double *)((char *)base + ctrl_bytes);
+        dev.rbuf_stride[r] = 3 * std::max<long long>(all[r].n_halo, 1);
+        dev.land_off[r] = all[r].recv_off[me];
+        dev.recv_cnt[r] = c->recv_cnt[r];
+        dev.send_off[r] = c->send_off[r];
+    }
+    dev.send_off[W] = c->n_send;
+    STAN_TRY(c->d_dev.alloc(1, s));
+    if (!c->d_ticket.p) {
+        STAN_TRY(c->d_ticket.alloc(1, s));
+        STAN_CUDA(cudaMemsetAsync(c->d_ticket.p, 0, sizeof(unsigned int), s));
+    }
+    STAN_CUDA(cudaMemcpyAsync(c->d_dev.p, &dev, sizeof dev, cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    c->p2p = true;
+    return STAN_OK;
 }
 
 int comm_build_halo(stan_handle *h) {
@@ -218,14 +386,23 @@ int comm_build_halo(stan_handle *h) {
         STAN_CUDA(cudaMemcpyAsync(c->d_send_rows.p, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaStreamSynchronize(s));
     h->launches += 4;
-    return STAN_OK;
+    return p2p_setup(h);
 }
 
 // vec holds 3*nloc owned entries followed by 3*n_halo halo entries
-int comm_halo_exchange(stan_handle *h, double *d_vec, cudaStream_t s) {
+int comm_halo_exchange(stan_handle *h, double *d_vec, cudaStream_t s, CgState *st) {
     if (h->world <= 1) return STAN_OK;
     Comm *c = h->comm;
     const int64_t nloc = h->row1 - h->row0;
+    if (c->p2p) {
+        const unsigned long long seq = ++c->halo_seq;
+        const int gp = (int)std::min<int64_t>(std::max<int64_t>(div_up(3 * c->n_send, 256), 1), 64);
+        k_halo_push<<<gp, 256, 0, s>>>(c->d_dev.p, c->d_send_rows.p, d_vec, seq, c->d_ticket.p, st);
+        const int gw = (int)std::min<int64_t>(std::max<int64_t>(div_up(3 * h->n_halo, 256), 1), 64);
+        k_halo_wait<<<gw, 256, 0, s>>>(c->d_dev.p, d_vec, 3 * nloc, 3 * h->n_halo, seq, st);
+        h->launches += 2;
+        return STAN_OK;
+    }
     if (c->n_send) {
         k_pack<<<div_up(3 * c->n_send, 256), 256, 0, s>>>(c->n_send, c->d_send_rows.p, d_vec, c->d_sendbuf.p);
         h->launches += 1;

@@ -59,6 +59,27 @@ struct DevBuf {
     }
 };
 
+// Peer-memory window of one rank (multi-GPU, comm.cu).  Every rank cudaMalloc's one window, the
+// ranks exchange CUDA IPC handles once per assemble, and from then on halo values and partial sums
+// travel as plain stores into the neighbour's window over NVLink — no collective library in the CG
+// loop.  Control block first, halo landing zones (double-buffered by exchange parity) after it.
+constexpr int P2P_MAX_RANKS = 32;
+struct P2PCtrl {
+    unsigned long long hflag[2][P2P_MAX_RANKS];   // halo arrival: sequence number per source rank
+    unsigned long long rflag[2][P2P_MAX_RANKS];   // reduction arrival
+    double red[2][P2P_MAX_RANKS][4];              // partial sums per source rank
+};
+struct CommDev {                                   // device-resident view used by kernels
+    int rank, world;
+    P2PCtrl *ctrl[P2P_MAX_RANKS];                 // ctrl[r]: window of rank r (own or IPC-mapped)
+    double *rbuf[P2P_MAX_RANKS];                  // rbuf[r]: landing zone of rank r, parity 0
+    long long rbuf_stride[P2P_MAX_RANKS];         // doubles between parity 0 and 1 of rank r
+    long long land_off[P2P_MAX_RANKS];            // where my rows start in rank r's landing zone (nodes)
+    long long send_off[P2P_MAX_RANKS + 1];        // my send list grouped by destination rank (nodes)
+    long long recv_cnt[P2P_MAX_RANKS];            // halo nodes I receive from rank r
+    int *err;                                      // device error flags of the handle
+};
+
 // Device-resident CG scalars: every decision ALGLIB's lincgiteration takes on the host is taken
 // here by one thread, so a batch of iterations can be enqueued without a host round trip.
 struct CgState {
@@ -77,6 +98,8 @@ struct CgState {
     int64_t restart;
     int32_t x_in_alt; // 1 when the accepted iterate lives in the alternate x buffer
     int32_t pad;
+    CommDev *comm;    // peer-memory reductions (multi-GPU P2P mode), else nullptr
+    unsigned long long red_seq;   // reductions published so far (same on every rank)
 };
 
 struct Comm;  // comm.cu
@@ -138,6 +161,7 @@ struct stan_handle {
     stan::DevBuf<stan::CgState> d_state;
     stan::DevBuf<unsigned int> d_counter;
     bool x_in_alt = false;
+    unsigned long long red_seq = 0;     // cross-rank reductions published so far (peer-memory mode)
 
     // ---- results ----
     stan::DevBuf<double> d_ufull;       // 3*n_nodes in DOF order (all ranks after the gather)
@@ -184,9 +208,11 @@ int comm_unique_id(void *id128);
 int comm_init(stan_handle *h, const void *id128);
 void comm_destroy(stan_handle *h);
 int comm_allreduce_sum(stan_handle *h, double *d_buf, int count, cudaStream_t s);
-int comm_halo_exchange(stan_handle *h, double *d_vec, cudaStream_t s);
+int comm_halo_exchange(stan_handle *h, double *d_vec, cudaStream_t s, CgState *st = nullptr);
 int comm_allgather_rows(stan_handle *h, const double *d_local, double *d_full, cudaStream_t s);
 int comm_build_halo(stan_handle *h);
+bool comm_p2p_active(const stan_handle *h);
+CommDev *comm_dev(const stan_handle *h);
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 

@@ -180,8 +180,8 @@ int build_system_pattern(stan_handle *h) {
     cudaStream_t s = h->stream;
     const int T = 256;
     const int64_t nn = h->n_nodes, ne = h->n_elem, nloc = h->row1 - h->row0;
-    STAN_TRY(h->d_err.alloc(4, s));
-    STAN_CUDA(cudaMemsetAsync(h->d_err.p, 0, 4 * sizeof(int32_t), s));
+    STAN_TRY(h->d_err.alloc(8, s));
+    STAN_CUDA(cudaMemsetAsync(h->d_err.p, 0, 8 * sizeof(int32_t), s));
 
     STAN_TRY(h->d_inv.alloc(nn, s));
     STAN_CUDA(cudaMemsetAsync(h->d_inv.p, 0xff, nn * sizeof(int32_t), s));

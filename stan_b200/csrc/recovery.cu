@@ -152,7 +152,7 @@ int run_recovery(stan_handle *h, stan_recovery_stats *stats) {
     const int64_t ne = h->elem1 - h->elem0;
     STAN_TRY(h->d_strain.alloc((size_t)48 * ne, s));
     STAN_TRY(h->d_stress.alloc((size_t)48 * ne, s));
-    STAN_CUDA(cudaMemsetAsync(h->d_err.p, 0, 4 * sizeof(int32_t), s));
+    STAN_CUDA(cudaMemsetAsync(h->d_err.p, 0, 8 * sizeof(int32_t), s));
     STAN_CUDA(cudaEventRecord(h->ev0, s));
     k_recover<<<div_up(8 * ne, REC_THREADS), REC_THREADS, 0, s>>>(
         h->elem0, ne, h->d_conn.p, h->d_xyz.p, h->d_node_index.p, h->d_etype.p, h->d_emat.p, h->d_lambda.p, h->d_G.p,
