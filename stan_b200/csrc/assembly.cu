@@ -202,6 +202,132 @@ k_assemble_rows(int64_t nloc, int64_t row0, const int32_t *__restrict__ inc_ptr,
     for (int t = tid; t < nvals; t += ASM_THREADS) out[t] = s_buf[t];
 }
 
+// ---- assembly, version 2: integrate, stage, gather by slot -------------------------------------
+// ncu on k_assemble_rows (profiles/r01_path_10m_ncu.md): 14 of 32 lanes active on average and the
+// eight barrier-separated accumulation rounds cost as much as the integration.  Here thread
+// (row r, rank k) = t integrates the k-th incident element of row r exactly as before, parks its
+// 3x24 row block in shared memory (column-major, conflict-free) and records, per (row, block slot),
+// which of its eight element columns land there (one mask byte per rank).  Then every thread owns
+// output entries and *gathers*: out(r, a, slot, b) = sum over ranks k ascending, columns j ascending
+// — the same fixed element order, no atomics, no serialised rounds, all lanes busy.  16 rows and
+// 128 threads per CTA keep two CTAs resident per SM so one integrates while the other gathers.
+constexpr int A2_ROWS = 16;
+constexpr int A2_THREADS = 128;
+constexpr int A2_STRIDE = A2_THREADS + 1;      // padded stride of the staged row blocks (doubles)
+
+__global__ void __launch_bounds__(A2_THREADS, 2)
+k_assemble_rows2(int64_t nloc, int64_t row0, const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
+                 const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
+                 const int32_t *__restrict__ conn, const double *__restrict__ xyz,
+                 const int32_t *__restrict__ node_index, const uint8_t *__restrict__ etype,
+                 const int32_t *__restrict__ emat, const double *__restrict__ lam_tab, const double *__restrict__ G_tab,
+                 const uint8_t *__restrict__ fixed, double *__restrict__ vals, double *__restrict__ d2, int32_t *err,
+                 int max_blocks) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    double *s_stage = reinterpret_cast<double *>(s_dyn);                       // [72][A2_STRIDE]
+    double *s_out = s_stage + 72 * A2_STRIDE;                                   // [9 * max_blocks]
+    unsigned long long *s_mask = reinterpret_cast<unsigned long long *>(s_out + 9 * max_blocks);   // [max_blocks]: 8 rank bytes
+    __shared__ double s_tab[9 * 24];
+    __shared__ int s_inc[A2_ROWS + 1], s_brow[A2_ROWS + 1];
+    const int tid = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * A2_ROWS;
+    const int nr = (int)((nloc - r0) < A2_ROWS ? (nloc - r0) : A2_ROWS);
+    if (tid <= nr) { s_inc[tid] = inc_ptr[r0 + tid]; s_brow[tid] = brow_ptr[r0 + tid]; }
+    for (int t = tid; t < 216; t += A2_THREADS) s_tab[t] = (&c_dNl[0][0])[t];
+    __syncthreads();
+    const int b0 = s_brow[0], nblk = s_brow[nr] - b0, nvals = 9 * nblk;
+    for (int t = tid; t < nvals; t += A2_THREADS) s_out[t] = 0.0;
+
+    const int r = tid >> 3, k = tid & 7;                    // row of the tile, rank slot
+    int maxcnt = 0;
+    for (int i = 0; i < nr; i++) maxcnt = max(maxcnt, s_inc[i + 1] - s_inc[i]);
+    for (int c0 = 0; c0 < maxcnt; c0 += 8) {                // rows with more than 8 incident elements: several passes
+        for (int t = tid; t < nblk; t += A2_THREADS) s_mask[t] = 0ull;
+        __syncthreads();
+        const int idx = (r < nr) ? s_inc[r] + c0 + k : 0;
+        const bool active = r < nr && idx < s_inc[r + 1];
+        if (active) {
+            const int ent = inc[idx];
+            const int64_t e = ent >> 3;
+            double X[24], K[72];
+            load_element(conn, xyz, e, X);
+            const int mat = emat[e];
+            if (hex8_row_block(etype[e], X, ent & 7, lam_tab[mat], G_tab[mat], s_tab, K)) atomicOr(err + 2, 1);
+#pragma unroll
+            for (int q = 0; q < 72; q++) s_stage[q * A2_STRIDE + tid] = K[q];
+            // which element column j lands in which block slot of row r
+            const int nb = s_brow[r + 1] - s_brow[r];
+            const int32_t *cols = bcol + s_brow[r];
+            unsigned char *mrow = reinterpret_cast<unsigned char *>(s_mask + (s_brow[r] - b0));
+            const int4 c0v = *reinterpret_cast<const int4 *>(conn + 8 * e);
+            const int4 c1v = *reinterpret_cast<const int4 *>(conn + 8 * e + 4);
+            const int nd[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int32_t q = node_index[nd[j]];
+                int lo = 0, hi = nb - 1;
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (cols[mid] < q) lo = mid + 1; else hi = mid;
+                }
+                mrow[8 * lo + k] |= (unsigned char)(1u << j);   // byte (slot, rank) belongs to this thread only
+            }
+        }
+        __syncthreads();
+        // gather: entry w of the tile's value storage = (row rr, scalar row a, slot s, column b)
+        for (int w = tid; w < nvals; w += A2_THREADS) {
+            int rr = 0;
+            while (rr + 1 < nr && 9 * (s_brow[rr + 1] - b0) <= w) rr++;
+            const int nbr = s_brow[rr + 1] - s_brow[rr];
+            const int local = w - 9 * (s_brow[rr] - b0);
+            const int a = local / (3 * nbr), rem = local - a * 3 * nbr;
+            const int s = rem / 3, b = rem - 3 * s;
+            unsigned long long m = s_mask[s_brow[rr] - b0 + s];
+            double sum = 0.0;
+            for (int kk = 0; kk < 8 && m; kk++, m >>= 8) {
+                unsigned int bits = (unsigned int)(m & 0xffull);
+                while (bits) {
+                    const int j = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    sum += s_stage[(a * 24 + 3 * j + b) * A2_STRIDE + rr * 8 + kk];
+                }
+            }
+            s_out[w] += sum;
+        }
+        __syncthreads();
+    }
+    // SPC masking (fixed rows/columns dropped, SolverFunctions.cs:158-160), identity on fixed rows, Jacobi scaling
+    for (int w = tid; w < nvals; w += A2_THREADS) {
+        int rr = 0;
+        while (rr + 1 < nr && 9 * (s_brow[rr + 1] - b0) <= w) rr++;
+        const int nbr = s_brow[rr + 1] - s_brow[rr];
+        const int local = w - 9 * (s_brow[rr] - b0);
+        const int a = local / (3 * nbr), rem = local - a * 3 * nbr;
+        const int s = rem / 3, b = rem - 3 * s;
+        const int64_t p = row0 + r0 + rr;
+        const int64_t q = bcol[s_brow[rr] + s];
+        const bool fr = fixed[3 * p + a] != 0, fc = fixed[3 * q + b] != 0;
+        if (fr || fc) s_out[w] = (fr && q == p && a == b) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (tid < 3 * nr) {
+        const int rl = tid / 3, a = tid % 3;
+        const int64_t p = row0 + r0 + rl;
+        const int nb = s_brow[rl + 1] - s_brow[rl];
+        const int32_t *cols = bcol + s_brow[rl];
+        int lo = 0, hi = nb - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (cols[mid] < (int32_t)p) lo = mid + 1; else hi = mid;
+        }
+        const double v = s_out[9 * (s_brow[rl] - b0) + a * 3 * nb + 3 * lo + a];
+        const double d = v > 0.0 ? 1.0 / sqrt(v) : 1.0;
+        d2[3 * (r0 + rl) + a] = d * d;
+    }
+    double *out = vals + 9 * (int64_t)b0;
+    for (int t = tid; t < nvals; t += A2_THREADS) out[t] = s_out[t];
+}
+
 // Element.K_Initial for a range of elements, 24x24 row-major each: one thread per matrix row block.
 __global__ void __launch_bounds__(128)
 k_element_ke(int64_t first, int64_t count, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
@@ -258,6 +384,22 @@ int run_assembly(stan_handle *h) {
     const int64_t nloc = h->row1 - h->row0;
     STAN_TRY(h->d_vals.alloc((size_t)9 * h->n_blocks + 2, s));   // +2: 16-byte granules of the bulk-copy SpMV
     STAN_TRY(h->d_d2.alloc(3 * nloc, s));
+    {   // version 2 (stage + gather) is opt-in (STAN_ASM=2): measured 180 ms vs 114 ms for version 1 on the 10M
+        // beam — decoding (row, scalar row, slot, column) per output entry costs more than the rounds it removes
+        static const int want = getenv("STAN_ASM") ? atoi(getenv("STAN_ASM")) : 1;
+        const int mb = h->max_group16 > 0 ? h->max_group16 : 1;
+        const size_t smem2 = (size_t)72 * A2_STRIDE * sizeof(double) + (size_t)mb * (72 + 8);
+        if (want == 2 && smem2 <= 220 * 1024) {
+            STAN_CUDA(cudaFuncSetAttribute(k_assemble_rows2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            k_assemble_rows2<<<div_up(nloc, A2_ROWS), A2_THREADS, smem2, s>>>(
+                nloc, h->row0, h->d_inc_ptr.p, h->d_inc.p, h->d_brow_ptr.p, h->d_bcol.p, h->d_conn.p, h->d_xyz.p,
+                h->d_node_index.p, h->d_etype.p, h->d_emat.p, h->d_lambda.p, h->d_G.p, h->d_fixed.p, h->d_vals.p,
+                h->d_d2.p, h->d_err.p, mb);
+            STAN_CUDA(cudaGetLastError());
+            h->launches += 1;
+            return STAN_OK;
+        }
+    }
     const size_t smem = (size_t)9 * h->max_group_blocks * sizeof(double);
     if (smem > 200 * 1024) {
         set_error("32 consecutive rows couple to %d blocks; the assembly tile holds at most %d", h->max_group_blocks,

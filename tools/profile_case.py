@@ -16,6 +16,7 @@ m = mesh.workload(name, tolerance=1e-8)
 with Solver() as s:
     s.SetModel(m)
     s.AssignDOF()
+    s.ParallelAssembly_K()            # first call pays pool growth and module load
     a = s.ParallelAssembly_K()
     cg = s.LinearSolver_CG(merit_check=0, IterMax=iters)
     r = s.Recovery_Stress()
