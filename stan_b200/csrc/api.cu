@@ -88,7 +88,7 @@ int stan_destroy(stan_handle *h) {
     h->d_b.release(s); h->d_d2.release(s); h->d_err.release(s); h->d_x.release(s); h->d_xalt.release(s);
     h->d_r.release(s); h->d_p.release(s); h->d_mv.release(s); h->d_partials.release(s); h->d_state.release(s);
     h->d_counter.release(s); h->d_ufull.release(s); h->d_strain.release(s); h->d_stress.release(s);
-    h->d_cell.release(s); h->d_point.release(s);
+    h->d_cell.release(s); h->d_point.release(s); h->d_ke.release(s);
     cudaStreamSynchronize(s);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
     for (int i = 0; i < 8; i++) if (h->user_ev[i]) cudaEventDestroy(h->user_ev[i]);

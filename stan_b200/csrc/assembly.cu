@@ -202,130 +202,227 @@ k_assemble_rows(int64_t nloc, int64_t row0, const int32_t *__restrict__ inc_ptr,
     for (int t = tid; t < nvals; t += ASM_THREADS) out[t] = s_buf[t];
 }
 
-// ---- assembly, version 2: integrate, stage, gather by slot -------------------------------------
-// ncu on k_assemble_rows (profiles/r01_path_10m_ncu.md): 14 of 32 lanes active on average and the
-// eight barrier-separated accumulation rounds cost as much as the integration.  Here thread
-// (row r, rank k) = t integrates the k-th incident element of row r exactly as before, parks its
-// 3x24 row block in shared memory (column-major, conflict-free) and records, per (row, block slot),
-// which of its eight element columns land there (one mask byte per rank).  Then every thread owns
-// output entries and *gathers*: out(r, a, slot, b) = sum over ranks k ascending, columns j ascending
-// — the same fixed element order, no atomics, no serialised rounds, all lanes busy.  16 rows and
-// 128 threads per CTA keep two CTAs resident per SM so one integrates while the other gathers.
-constexpr int A2_ROWS = 16;
-constexpr int A2_THREADS = 128;
-constexpr int A2_STRIDE = A2_THREADS + 1;      // padded stride of the staged row blocks (doubles)
+// ---- assembly, two-kernel path: integrate every element once, then gather rows ------------------
+// ncu on k_assemble_rows (profiles/r01_path_10m_ncu.md): FP64 pipe 16 %, 14 of 32 lanes active, and every
+// element is integrated once per incident node (2.8x the flops).  The two kernels below restore the
+// textbook split while staying deterministic:
+//
+//   k_hex8_ke_batch  one CTA per batch of 8 elements.  Phase 1: thread (element, Gauss point) forms J,
+//                    J^-1 and the global shape-function derivatives once and stages dN (8x3) and w|J|
+//                    in shared memory.  Phase 2: thread (element, upper block (i <= j)) contracts the
+//                    staged derivatives over the Gauss points into one 3x3 block — 9 accumulators, so
+//                    the kernel runs at high occupancy — and stores the 36 upper blocks of Ke (2592 B per
+//                    element) with fully coalesced writes.  Ke is symmetric by construction.
+//   k_assemble_gather  one warp per matrix row, lanes = block slots.  It walks the row's incident
+//                    (element, local node i) entries in ascending order, finds which element column j
+//                    lands in each lane's slot with eight shuffles, and adds Ke block (i, j) (or the
+//                    transpose of (j, i)) — fixed order, no atomics, every stored value written once,
+//                    coalesced.  The incidence list is the element-to-slot map.
+constexpr int KB_ELEMS = 8;                       // elements per CTA
+constexpr int KB_THREADS = KB_ELEMS * 36;         // one thread per upper block in phase 2
+__constant__ unsigned char c_blk_i[36], c_blk_j[36];
 
-__global__ void __launch_bounds__(A2_THREADS, 2)
-k_assemble_rows2(int64_t nloc, int64_t row0, const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
-                 const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
-                 const int32_t *__restrict__ conn, const double *__restrict__ xyz,
-                 const int32_t *__restrict__ node_index, const uint8_t *__restrict__ etype,
-                 const int32_t *__restrict__ emat, const double *__restrict__ lam_tab, const double *__restrict__ G_tab,
-                 const uint8_t *__restrict__ fixed, double *__restrict__ vals, double *__restrict__ d2, int32_t *err,
-                 int max_blocks) {
-    extern __shared__ __align__(16) unsigned char s_dyn[];
-    double *s_stage = reinterpret_cast<double *>(s_dyn);                       // [72][A2_STRIDE]
-    double *s_out = s_stage + 72 * A2_STRIDE;                                   // [9 * max_blocks]
-    unsigned long long *s_mask = reinterpret_cast<unsigned long long *>(s_out + 9 * max_blocks);   // [max_blocks]: 8 rank bytes
-    __shared__ double s_tab[9 * 24];
-    __shared__ int s_inc[A2_ROWS + 1], s_brow[A2_ROWS + 1];
+__device__ __forceinline__ int upper_index(int i, int j) { return i * 8 - (i * (i - 1)) / 2 + (j - i); }   // i <= j
+
+__global__ void __launch_bounds__(KB_THREADS)
+k_hex8_ke_batch(int64_t n_local, const int32_t *__restrict__ lelem, const int32_t *__restrict__ conn,
+                const double *__restrict__ xyz, const uint8_t *__restrict__ etype, const int32_t *__restrict__ emat,
+                const double *__restrict__ lam_tab, const double *__restrict__ G_tab, double *__restrict__ ke_store,
+                int32_t *err) {
+    __shared__ double s_dn[KB_ELEMS][8][25];       // per (element, Gauss point): dN[node][xyz] and w|J|
+    __shared__ double s_lam[KB_ELEMS], s_G[KB_ELEMS];
+    __shared__ int s_ng[KB_ELEMS];
     const int tid = threadIdx.x;
-    const int64_t r0 = (int64_t)blockIdx.x * A2_ROWS;
-    const int nr = (int)((nloc - r0) < A2_ROWS ? (nloc - r0) : A2_ROWS);
-    if (tid <= nr) { s_inc[tid] = inc_ptr[r0 + tid]; s_brow[tid] = brow_ptr[r0 + tid]; }
-    for (int t = tid; t < 216; t += A2_THREADS) s_tab[t] = (&c_dNl[0][0])[t];
+    const int64_t le0 = (int64_t)blockIdx.x * KB_ELEMS;
+    if (tid < KB_ELEMS * 8) {                      // ---- phase 1: Jacobians and derivatives, once per (e, g)
+        const int el = tid >> 3, g = tid & 7;
+        const int64_t le = le0 + el;
+        if (le < n_local) {
+            const int64_t e = lelem ? lelem[le] : le;
+            const int type = etype[e];
+            const int ng = (type == STAN_HEX8_G2) ? 8 : 1;
+            if (g == 0) { s_ng[el] = ng; const int mat = emat[e]; s_lam[el] = lam_tab[mat]; s_G[el] = G_tab[mat]; }
+            if (g < ng) {
+                const int gp = (type == STAN_HEX8_G2) ? g : 8;
+                const double w = (type == STAN_HEX8_G2) ? 1.0 : 8.0;
+                double X[24];
+                load_element(conn, xyz, e, X);
+                double J[9];
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) sum += c_dNl[gp][r * 8 + k] * X[k * 3 + c];
+                        J[r * 3 + c] = sum;
+                    }
+                const double det = det3(J);
+                if (det == 0.0) atomicOr(err + 2, 1);
+                const double inv = 1.0 / det;
+                double Ji[9];
+                Ji[0] = inv * (J[4] * J[8] - J[5] * J[7]);
+                Ji[1] = inv * (J[2] * J[7] - J[1] * J[8]);
+                Ji[2] = inv * (J[1] * J[5] - J[2] * J[4]);
+                Ji[3] = inv * (J[5] * J[6] - J[3] * J[8]);
+                Ji[4] = inv * (J[0] * J[8] - J[2] * J[6]);
+                Ji[5] = inv * (J[2] * J[3] - J[0] * J[5]);
+                Ji[6] = inv * (J[3] * J[7] - J[4] * J[6]);
+                Ji[7] = inv * (J[1] * J[6] - J[0] * J[7]);
+                Ji[8] = inv * (J[0] * J[4] - J[1] * J[3]);
+                double *out = s_dn[el][g];
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        out[3 * k + c] = Ji[c * 3 + 0] * c_dNl[gp][k] + Ji[c * 3 + 1] * c_dNl[gp][8 + k] + Ji[c * 3 + 2] * c_dNl[gp][16 + k];
+                out[24] = det * w;
+            }
+        }
+    }
     __syncthreads();
-    const int b0 = s_brow[0], nblk = s_brow[nr] - b0, nvals = 9 * nblk;
-    for (int t = tid; t < nvals; t += A2_THREADS) s_out[t] = 0.0;
+    // ---- phase 2: one upper block per thread, contracted over the Gauss points ----
+    const int el = tid / 36, blk = tid - 36 * el;
+    const int64_t le = le0 + el;
+    if (le >= n_local) return;
+    const int i = c_blk_i[blk], j = c_blk_j[blk];
+    const double lam = s_lam[el], G = s_G[el];
+    double K[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) K[q] = 0.0;
+    const int ng = s_ng[el];
+    for (int g = 0; g < ng; g++) {
+        const double *d = s_dn[el][g];
+        const double wdet = d[24];
+        const double di0 = d[3 * i], di1 = d[3 * i + 1], di2 = d[3 * i + 2];
+        const double dj[3] = {d[3 * j], d[3 * j + 1], d[3 * j + 2]};
+        const double l[3] = {lam * wdet * di0, lam * wdet * di1, lam * wdet * di2};
+        const double u[3] = {G * wdet * di0, G * wdet * di1, G * wdet * di2};
+        const double sdot = u[0] * dj[0] + u[1] * dj[1] + u[2] * dj[2];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+#pragma unroll
+            for (int b = 0; b < 3; b++) K[3 * a + b] += l[a] * dj[b] + u[b] * dj[a];
+            K[3 * a + a] += sdot;
+        }
+    }
+    double *out = ke_store + (le * 36 + blk) * 9;
+#pragma unroll
+    for (int q = 0; q < 9; q++) out[q] = K[q];
+}
 
-    const int r = tid >> 3, k = tid & 7;                    // row of the tile, rank slot
-    int maxcnt = 0;
-    for (int i = 0; i < nr; i++) maxcnt = max(maxcnt, s_inc[i + 1] - s_inc[i]);
-    for (int c0 = 0; c0 < maxcnt; c0 += 8) {                // rows with more than 8 incident elements: several passes
-        for (int t = tid; t < nblk; t += A2_THREADS) s_mask[t] = 0ull;
-        __syncthreads();
-        const int idx = (r < nr) ? s_inc[r] + c0 + k : 0;
-        const bool active = r < nr && idx < s_inc[r + 1];
-        if (active) {
-            const int ent = inc[idx];
-            const int64_t e = ent >> 3;
-            double X[24], K[72];
-            load_element(conn, xyz, e, X);
-            const int mat = emat[e];
-            if (hex8_row_block(etype[e], X, ent & 7, lam_tab[mat], G_tab[mat], s_tab, K)) atomicOr(err + 2, 1);
+constexpr int GA_WARPS = 8;
+constexpr int GA_GROUP = 4;                       // incidence entries whose blocks are in flight together
+
+__global__ void __launch_bounds__(32 * GA_WARPS, 2)
+k_assemble_gather(int64_t nloc, int64_t row0, const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
+                  const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
+                  const int32_t *__restrict__ conn, const int32_t *__restrict__ node_index,
+                  const int32_t *__restrict__ g2l, const double *__restrict__ ke_store,
+                  const uint8_t *__restrict__ fixed, double *__restrict__ vals, double *__restrict__ d2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t rl = (int64_t)blockIdx.x * GA_WARPS + (threadIdx.x >> 5);
+    if (rl >= nloc) return;
+    const int64_t p = row0 + rl;
+    const int s0 = brow_ptr[rl], nb = brow_ptr[rl + 1] - s0;
+    const int t0 = inc_ptr[rl], t1 = inc_ptr[rl + 1];
+    const bool fr[3] = {fixed[3 * p] != 0, fixed[3 * p + 1] != 0, fixed[3 * p + 2] != 0};
+    for (int sb = 0; sb < nb; sb += 32) {          // one pass unless the row has more than 32 blocks
+        const int s = sb + lane;
+        const bool have = s < nb;
+        const int32_t myq = have ? bcol[s0 + s] : -1;
+        double acc[9];
 #pragma unroll
-            for (int q = 0; q < 72; q++) s_stage[q * A2_STRIDE + tid] = K[q];
-            // which element column j lands in which block slot of row r
-            const int nb = s_brow[r + 1] - s_brow[r];
-            const int32_t *cols = bcol + s_brow[r];
-            unsigned char *mrow = reinterpret_cast<unsigned char *>(s_mask + (s_brow[r] - b0));
-            const int4 c0v = *reinterpret_cast<const int4 *>(conn + 8 * e);
-            const int4 c1v = *reinterpret_cast<const int4 *>(conn + 8 * e + 4);
-            const int nd[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+        for (int q = 0; q < 9; q++) acc[q] = 0.0;
+        // Entries are taken GA_GROUP at a time.  Pass 1 finds, per entry, which element columns fall into this
+        // lane's slot (a bit mask; more than one bit only for degenerate elements that repeat a node) and
+        // where the block lives; pass 2 loads the blocks — independent 72-byte reads in flight — and
+        // adds them in ascending (element, local node, column) order: the fixed summation order.
+        for (int tg = t0; tg < t1; tg += GA_GROUP) {
+            const double *blk[GA_GROUP];
+            int bits[GA_GROUP], irow[GA_GROUP];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const int32_t q = node_index[nd[j]];
-                int lo = 0, hi = nb - 1;
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (cols[mid] < q) lo = mid + 1; else hi = mid;
-                }
-                mrow[8 * lo + k] |= (unsigned char)(1u << j);   // byte (slot, rank) belongs to this thread only
-            }
-        }
-        __syncthreads();
-        // gather: entry w of the tile's value storage = (row rr, scalar row a, slot s, column b)
-        for (int w = tid; w < nvals; w += A2_THREADS) {
-            int rr = 0;
-            while (rr + 1 < nr && 9 * (s_brow[rr + 1] - b0) <= w) rr++;
-            const int nbr = s_brow[rr + 1] - s_brow[rr];
-            const int local = w - 9 * (s_brow[rr] - b0);
-            const int a = local / (3 * nbr), rem = local - a * 3 * nbr;
-            const int s = rem / 3, b = rem - 3 * s;
-            unsigned long long m = s_mask[s_brow[rr] - b0 + s];
-            double sum = 0.0;
-            for (int kk = 0; kk < 8 && m; kk++, m >>= 8) {
-                unsigned int bits = (unsigned int)(m & 0xffull);
-                while (bits) {
-                    const int j = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    sum += s_stage[(a * 24 + 3 * j + b) * A2_STRIDE + rr * 8 + kk];
+            for (int u = 0; u < GA_GROUP; u++) {
+                bits[u] = 0; irow[u] = 0; blk[u] = ke_store;
+                if (tg + u < t1) {                  // warp-uniform
+                    const int ent = inc[tg + u];
+                    const int64_t e = ent >> 3;
+                    const int32_t qj_mine = node_index[conn[8 * e + (lane & 7)]];
+                    int m = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if (__shfl_sync(0xffffffffu, qj_mine, j) == myq) m |= 1 << j;
+                    bits[u] = have ? m : 0;
+                    irow[u] = ent & 7;
+                    blk[u] = ke_store + (int64_t)(g2l ? g2l[e] : e) * 324;
                 }
             }
-            s_out[w] += sum;
+            double v[GA_GROUP][9];
+#pragma unroll
+            for (int u = 0; u < GA_GROUP; u++) {
+                if (bits[u]) {
+                    const int j = __ffs(bits[u]) - 1, i = irow[u];
+                    const double *src = blk[u] + (i <= j ? upper_index(i, j) : upper_index(j, i)) * 9;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) v[u][q] = src[q];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < GA_GROUP; u++) {
+                if (bits[u]) {
+                    int rest = bits[u];
+                    const int i = irow[u];
+                    int j = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    if (i <= j) {
+#pragma unroll
+                        for (int q = 0; q < 9; q++) acc[q] += v[u][q];
+                    } else {                        // lower block = transpose of the stored upper one
+#pragma unroll
+                        for (int a = 0; a < 3; a++)
+#pragma unroll
+                            for (int b = 0; b < 3; b++) acc[3 * a + b] += v[u][3 * b + a];
+                    }
+                    while (rest) {                  // degenerate element: the node appears again at column j
+                        j = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        const double *src = blk[u] + (i <= j ? upper_index(i, j) : upper_index(j, i)) * 9;
+                        for (int a = 0; a < 3; a++)
+                            for (int b = 0; b < 3; b++) acc[3 * a + b] += (i <= j) ? src[3 * a + b] : src[3 * b + a];
+                    }
+                }
+            }
         }
-        __syncthreads();
-    }
-    // SPC masking (fixed rows/columns dropped, SolverFunctions.cs:158-160), identity on fixed rows, Jacobi scaling
-    for (int w = tid; w < nvals; w += A2_THREADS) {
-        int rr = 0;
-        while (rr + 1 < nr && 9 * (s_brow[rr + 1] - b0) <= w) rr++;
-        const int nbr = s_brow[rr + 1] - s_brow[rr];
-        const int local = w - 9 * (s_brow[rr] - b0);
-        const int a = local / (3 * nbr), rem = local - a * 3 * nbr;
-        const int s = rem / 3, b = rem - 3 * s;
-        const int64_t p = row0 + r0 + rr;
-        const int64_t q = bcol[s_brow[rr] + s];
-        const bool fr = fixed[3 * p + a] != 0, fc = fixed[3 * q + b] != 0;
-        if (fr || fc) s_out[w] = (fr && q == p && a == b) ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    if (tid < 3 * nr) {
-        const int rl = tid / 3, a = tid % 3;
-        const int64_t p = row0 + r0 + rl;
-        const int nb = s_brow[rl + 1] - s_brow[rl];
-        const int32_t *cols = bcol + s_brow[rl];
-        int lo = 0, hi = nb - 1;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (cols[mid] < (int32_t)p) lo = mid + 1; else hi = mid;
+        if (have) {
+            const uint8_t *fq = fixed + 3 * (int64_t)myq;
+            double *out = vals + 9 * (int64_t)s0 + 3 * s;
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) {
+                    double v = acc[3 * a + b];
+                    if (fr[a] || fq[b]) v = (fr[a] && myq == (int32_t)p && a == b) ? 1.0 : 0.0;   // SPC rows/columns
+                    out[(int64_t)a * 3 * nb + b] = v;
+                    if (myq == (int32_t)p && a == b) {                                              // Jacobi scaling
+                        const double d = v > 0.0 ? 1.0 / sqrt(v) : 1.0;
+                        d2[3 * rl + a] = d * d;
+                    }
+                }
         }
-        const double v = s_out[9 * (s_brow[rl] - b0) + a * 3 * nb + 3 * lo + a];
-        const double d = v > 0.0 ? 1.0 / sqrt(v) : 1.0;
-        d2[3 * (r0 + rl) + a] = d * d;
     }
-    double *out = vals + 9 * (int64_t)b0;
-    for (int t = tid; t < nvals; t += A2_THREADS) out[t] = s_out[t];
+}
+
+__global__ void k_flag_local_elems(int64_t n_inc, const int32_t *__restrict__ inc, int32_t *__restrict__ flag) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n_inc) flag[inc[t] >> 3] = 1;
+}
+
+__global__ void k_compact_local_elems(int64_t n_elem, const int32_t *__restrict__ flag, const int32_t *__restrict__ pos,
+                                      int32_t *__restrict__ g2l, int32_t *__restrict__ lelem) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n_elem) return;
+    if (flag[e]) { g2l[e] = pos[e]; lelem[pos[e]] = (int32_t)e; }
+    else g2l[e] = -1;
 }
 
 // Element.K_Initial for a range of elements, 24x24 row-major each: one thread per matrix row block.
@@ -379,26 +476,71 @@ int upload_fe_tables() {
     return STAN_OK;
 }
 
+// Returns 0 when the matrix was assembled, 1 when the caller should use the fused kernel instead
+// (Ke store does not fit), < 0 on error.
+static int run_assembly_two_kernel(stan_handle *h) {
+    cudaStream_t s = h->stream;
+    const int64_t nloc = h->row1 - h->row0;
+    static bool tables = false;
+    if (!tables) {
+        unsigned char bi[36], bj[36];
+        int n = 0;
+        for (int i = 0; i < 8; i++) for (int j = i; j < 8; j++) { bi[n] = (unsigned char)i; bj[n] = (unsigned char)j; n++; }
+        STAN_CUDA(cudaMemcpyToSymbol(c_blk_i, bi, sizeof bi));
+        STAN_CUDA(cudaMemcpyToSymbol(c_blk_j, bj, sizeof bj));
+        tables = true;
+    }
+    // elements that touch an owned row: all of them on one GPU, a compacted list otherwise
+    int64_t n_local = h->n_elem;
+    DevBuf<int32_t> g2l, lelem;
+    if (h->world > 1) {
+        int32_t n_inc = 0;
+        STAN_CUDA(cudaMemcpyAsync(&n_inc, h->d_inc_ptr.p + nloc, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        DevBuf<int32_t> flag, pos;
+        STAN_TRY(flag.alloc(h->n_elem + 1, s)); STAN_TRY(pos.alloc(h->n_elem + 1, s)); STAN_TRY(g2l.alloc(h->n_elem, s));
+        STAN_CUDA(cudaMemsetAsync(flag.p, 0, (h->n_elem + 1) * sizeof(int32_t), s));
+        STAN_CUDA(cudaStreamSynchronize(s));
+        k_flag_local_elems<<<div_up(n_inc, 256), 256, 0, s>>>(n_inc, h->d_inc.p, flag.p);
+        STAN_TRY(device_exclusive_scan_i32(flag.p, pos.p, h->n_elem + 1, s));
+        int32_t cnt = 0;
+        STAN_CUDA(cudaMemcpyAsync(&cnt, pos.p + h->n_elem, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        STAN_CUDA(cudaStreamSynchronize(s));
+        n_local = cnt;
+        STAN_TRY(lelem.alloc(n_local, s));
+        k_compact_local_elems<<<div_up(h->n_elem, 256), 256, 0, s>>>(h->n_elem, flag.p, pos.p, g2l.p, lelem.p);
+        flag.release(s); pos.release(s);
+        h->launches += 3;
+    }
+    size_t free_b = 0, total_b = 0;
+    const size_t need = (size_t)n_local * 324 * sizeof(double);
+    cudaMemGetInfo(&free_b, &total_b);
+    if (h->d_ke.n * sizeof(double) < need && need + ((size_t)2 << 30) > free_b) {   // would not fit next to the matrix
+        g2l.release(s); lelem.release(s);
+        return 1;
+    }
+    STAN_TRY(h->d_ke.alloc((size_t)n_local * 324, s));
+    k_hex8_ke_batch<<<div_up(n_local, KB_ELEMS), KB_THREADS, 0, s>>>(n_local, h->world > 1 ? lelem.p : nullptr, h->d_conn.p,
+                                                                    h->d_xyz.p, h->d_etype.p, h->d_emat.p, h->d_lambda.p,
+                                                                    h->d_G.p, h->d_ke.p, h->d_err.p);
+    k_assemble_gather<<<div_up(nloc, GA_WARPS), 32 * GA_WARPS, 0, s>>>(nloc, h->row0, h->d_inc_ptr.p, h->d_inc.p,
+                                                                       h->d_brow_ptr.p, h->d_bcol.p, h->d_conn.p,
+                                                                       h->d_node_index.p, h->world > 1 ? g2l.p : nullptr,
+                                                                       h->d_ke.p, h->d_fixed.p, h->d_vals.p, h->d_d2.p);
+    STAN_CUDA(cudaGetLastError());
+    g2l.release(s); lelem.release(s);
+    h->launches += 2;
+    return 0;
+}
+
 int run_assembly(stan_handle *h) {
     cudaStream_t s = h->stream;
     const int64_t nloc = h->row1 - h->row0;
     STAN_TRY(h->d_vals.alloc((size_t)9 * h->n_blocks + 2, s));   // +2: 16-byte granules of the bulk-copy SpMV
     STAN_TRY(h->d_d2.alloc(3 * nloc, s));
-    {   // version 2 (stage + gather) is opt-in (STAN_ASM=2): measured 180 ms vs 114 ms for version 1 on the 10M
-        // beam — decoding (row, scalar row, slot, column) per output entry costs more than the rounds it removes
-        static const int want = getenv("STAN_ASM") ? atoi(getenv("STAN_ASM")) : 1;
-        const int mb = h->max_group16 > 0 ? h->max_group16 : 1;
-        const size_t smem2 = (size_t)72 * A2_STRIDE * sizeof(double) + (size_t)mb * (72 + 8);
-        if (want == 2 && smem2 <= 220 * 1024) {
-            STAN_CUDA(cudaFuncSetAttribute(k_assemble_rows2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            k_assemble_rows2<<<div_up(nloc, A2_ROWS), A2_THREADS, smem2, s>>>(
-                nloc, h->row0, h->d_inc_ptr.p, h->d_inc.p, h->d_brow_ptr.p, h->d_bcol.p, h->d_conn.p, h->d_xyz.p,
-                h->d_node_index.p, h->d_etype.p, h->d_emat.p, h->d_lambda.p, h->d_G.p, h->d_fixed.p, h->d_vals.p,
-                h->d_d2.p, h->d_err.p, mb);
-            STAN_CUDA(cudaGetLastError());
-            h->launches += 1;
-            return STAN_OK;
-        }
+    {   // two-kernel path unless the Ke store does not fit in free memory or STAN_ASM=1 asks for the fused kernel
+        static const int want = getenv("STAN_ASM") ? atoi(getenv("STAN_ASM")) : 2;
+        int rc = want == 2 ? run_assembly_two_kernel(h) : 1;
+        if (rc <= 0) return rc;                    // 0 = done, < 0 = error, 1 = fall through to the fused kernel
     }
     const size_t smem = (size_t)9 * h->max_group_blocks * sizeof(double);
     if (smem > 200 * 1024) {

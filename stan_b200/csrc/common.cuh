@@ -146,6 +146,7 @@ struct stan_handle {
     stan::DevBuf<int32_t> d_bcol;       // global BFS column node of every block
     stan::DevBuf<int32_t> d_bcol_loc;   // local x index of every block (owned: q-row0, halo: nloc+slot)
     const int32_t *bcol_x = nullptr;    // what SpMV indexes x with: d_bcol (1 GPU) or d_bcol_loc
+    stan::DevBuf<double> d_ke;          // 36 upper 3x3 blocks per local element (assembly scratch, kept in the pool)
     stan::DevBuf<double> d_vals;        // 9 per block; per block row: 3 scalar rows of length 3*nb
     stan::DevBuf<uint8_t> d_fixed;      // 3*n_nodes (global): 1 = SPC-fixed DOF
     stan::DevBuf<int32_t> d_red;        // 3*n_nodes: nDOF_reduction (Solver.cs:121-132)
@@ -181,6 +182,7 @@ int assign_dof_host(int64_t n_nodes, int64_t n_elem, const int32_t *conn, int32_
 // pattern.cu
 int build_system_pattern(stan_handle *h);
 int build_rhs(stan_handle *h);
+int device_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s);
 int export_csr_upper_size(stan_handle *h, int64_t *n, int64_t *nnz);
 int export_csr_upper(stan_handle *h, int64_t *rowptr, int32_t *col, double *val);
 

@@ -176,6 +176,10 @@ int exclusive_scan(const T *in, T *out, int64_t n, cudaStream_t s) {
 
 }  // namespace
 
+int device_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
+    return exclusive_scan(in, out, n, s);
+}
+
 int build_system_pattern(stan_handle *h) {
     cudaStream_t s = h->stream;
     const int T = 256;
