@@ -2,6 +2,7 @@
 // host<->device copies at the boundary.  Orchestrates pattern.cu / assembly.cu / cg.cu / recovery.cu
 // in the order of Solver.SolverLinearStatics (/root/reference/src/STAN_Solver/Solver.cs:97-210).
 #include <cmath>
+#include <thread>
 
 #include "common.cuh"
 
@@ -22,6 +23,49 @@ static int check(stan_handle *h) {
     if (!h) { set_error("null handle"); return STAN_E_ARG; }
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e)); return STAN_E_CUDA; }
+    return STAN_OK;
+}
+
+// Large results go to the caller's (pageable, usually untouched) buffer through two pinned staging
+// buffers: the DMA engine fills one while several host threads copy the other out — first-touch page
+// faults on the destination are what bound a plain cudaMemcpy to ~4 GB/s.
+static int copy_to_host(stan_handle *h, void *dst, const void *d_src, size_t bytes) {
+    cudaStream_t s = h->stream;
+    const size_t CH = (size_t)64 << 20;
+    if (bytes < 2 * CH) {
+        STAN_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, s));
+        STAN_CUDA(cudaStreamSynchronize(s));
+        return STAN_OK;
+    }
+    if (!h->stage[0]) {
+        for (int k = 0; k < 2; k++) {
+            STAN_CUDA(cudaMallocHost(&h->stage[k], CH));
+            STAN_CUDA(cudaEventCreateWithFlags(&h->stage_ev[k], cudaEventDisableTiming));
+        }
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nt = (int)std::min<unsigned>(8, hw ? hw : 1);
+    const size_t nch = (bytes + CH - 1) / CH;
+    auto issue = [&](size_t c) -> cudaError_t {
+        const size_t off = c * CH, n = std::min(CH, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(h->stage[c & 1], (const char *)d_src + off, n, cudaMemcpyDeviceToHost, s);
+        return e != cudaSuccess ? e : cudaEventRecord(h->stage_ev[c & 1], s);
+    };
+    STAN_CUDA(issue(0));
+    for (size_t c = 0; c < nch; c++) {
+        if (c + 1 < nch) STAN_CUDA(issue(c + 1));            // buffer (c+1)&1 was drained in the previous round
+        STAN_CUDA(cudaEventSynchronize(h->stage_ev[c & 1]));
+        const size_t off = c * CH, n = std::min(CH, bytes - off);
+        std::vector<std::thread> th;
+        const size_t per = ((n + nt - 1) / nt + 4095) & ~(size_t)4095;
+        for (int t = 0; t < nt; t++) {
+            const size_t a = (size_t)t * per;
+            if (a >= n) break;
+            const size_t len = std::min(per, n - a);
+            th.emplace_back([=] { memcpy((char *)dst + off + a, (const char *)h->stage[c & 1] + a, len); });
+        }
+        for (auto &t : th) t.join();
+    }
     return STAN_OK;
 }
 
@@ -92,6 +136,7 @@ int stan_destroy(stan_handle *h) {
     cudaStreamSynchronize(s);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
     for (int i = 0; i < 8; i++) if (h->user_ev[i]) cudaEventDestroy(h->user_ev[i]);
+    for (int k = 0; k < 2; k++) if (h->stage[k]) { cudaFreeHost(h->stage[k]); cudaEventDestroy(h->stage_ev[k]); }
     cudaStreamDestroy(h->stream); cudaStreamDestroy(h->comm_stream);
     delete h;
     return STAN_OK;
@@ -275,18 +320,15 @@ int stan_get_displacements(stan_handle *h, double *u_full) {
     if (!h->solved) { set_error("no solution yet"); return STAN_E_STATE; }
     if (!u_full) { set_error("null output"); return STAN_E_ARG; }
     if (!h->recovered) STAN_TRY(scatter_solution(h));
-    STAN_CUDA(cudaMemcpyAsync(u_full, h->d_ufull.p, 3 * h->n_nodes * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    STAN_CUDA(cudaStreamSynchronize(h->stream));
-    return STAN_OK;
+    return copy_to_host(h, u_full, h->d_ufull.p, 3 * h->n_nodes * sizeof(double));
 }
 
 int stan_get_strain_stress(stan_handle *h, double *strain, double *stress) {
     STAN_TRY(check(h));
     if (!h->recovered) { set_error("stan_get_strain_stress before stan_recover"); return STAN_E_STATE; }
     const size_t bytes = (size_t)48 * (h->elem1 - h->elem0) * sizeof(double);
-    if (strain) STAN_CUDA(cudaMemcpyAsync(strain, h->d_strain.p, bytes, cudaMemcpyDeviceToHost, h->stream));
-    if (stress) STAN_CUDA(cudaMemcpyAsync(stress, h->d_stress.p, bytes, cudaMemcpyDeviceToHost, h->stream));
-    STAN_CUDA(cudaStreamSynchronize(h->stream));
+    if (strain) STAN_TRY(copy_to_host(h, strain, h->d_strain.p, bytes));
+    if (stress) STAN_TRY(copy_to_host(h, stress, h->d_stress.p, bytes));
     return STAN_OK;
 }
 

@@ -114,6 +114,8 @@ struct stan_handle {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t user_ev[8] = {};
+    void *stage[2] = {nullptr, nullptr};   // pinned staging for large device-to-host results
+    cudaEvent_t stage_ev[2] = {};
 
     // ---- model (global, every rank holds the whole mesh) ----
     int64_t n_nodes = 0, n_elem = 0;
