@@ -171,11 +171,10 @@ int stan_set_mesh(stan_handle *h, int64_t n_nodes, const double *xyz, int64_t n_
     STAN_CUDA(cudaStreamSynchronize(s));
     int32_t mmax = 0;
     for (int64_t e = 0; e < n_elem; e++) { if (elem_mat[e] < 0) { set_error("negative material index"); return STAN_E_ARG; } mmax = std::max(mmax, elem_mat[e]); }
-    h->n_mat = std::max(h->n_mat, 0);
+    h->max_mat_index = mmax;
     h->have_mesh = true;
     h->have_dof = h->assembled = h->solved = h->recovered = h->postprocessed = false;
     h->h_spc_node.clear(); h->h_spc_val.clear(); h->h_load_node.clear(); h->h_load_val.clear();
-    (void)mmax;
     return STAN_OK;
 }
 
@@ -250,6 +249,10 @@ int stan_assemble(stan_handle *h, stan_assembly_stats *stats) {
     STAN_TRY(check(h));
     if (!h->have_mesh || !h->have_mat || !h->have_dof) {
         set_error("stan_assemble needs mesh, materials and a dof map"); return STAN_E_STATE;
+    }
+    if (h->max_mat_index >= h->n_mat) {                       // DB.MatLib[MatID] would throw KeyNotFound
+        set_error("an element uses material index %d but only %d materials were set", h->max_mat_index, h->n_mat);
+        return STAN_E_ARG;
     }
     cudaStream_t s = h->stream;
     const int64_t launches0 = h->launches;

@@ -119,7 +119,7 @@ struct stan_handle {
 
     // ---- model (global, every rank holds the whole mesh) ----
     int64_t n_nodes = 0, n_elem = 0;
-    int32_t n_mat = 0;
+    int32_t n_mat = 0, max_mat_index = 0;
     bool have_mesh = false, have_mat = false, have_dof = false, assembled = false, solved = false,
          recovered = false;
     std::vector<int32_t> h_conn;        // kept for the native AssignDOF only

@@ -141,3 +141,45 @@ def write_bdf(model: Model, path: str) -> None:
             a = "".join(f"{int(v):8d}" for v in nodes[:6])
             b = "".join(f"{int(v):8d}" for v in nodes[6:])
             fh.write(f"CHEXA   {e:8d}{int(pid):8d}{a}+\n+       {b}\n")
+
+
+def polar_disk(n_sectors: int, n_rings: int, nz: int, *, r_outer: float = 10.0, height: float = 5.0,
+               elem_type: int = HEX8_G2, E: float = 210000.0, nu: float = 0.3, tolerance: float = 1.0e-8) -> Model:
+    """Unstructured-valence test mesh: a disk meshed in polar fashion, extruded in z.
+
+    The axis nodes touch 2*n_sectors elements (far more than the 8 of a structured grid) and the
+    innermost ring consists of hexahedra collapsed to wedges — the axis node appears twice in their
+    connectivity — so rows with many blocks, many incident elements and degenerate elements are all
+    exercised.  Bottom face (z = 0) clamped, outer rim of the top face loaded in +x.
+    """
+    def nid(k, s, l):                         # ring k (0 = axis), sector s, layer l
+        if k == 0:
+            return l
+        return (nz + 1) + ((l * n_rings) + (k - 1)) * n_sectors + (s % n_sectors)
+
+    n_nodes = (nz + 1) * (1 + n_rings * n_sectors)
+    xyz = np.zeros((n_nodes, 3))
+    for l in range(nz + 1):
+        z = height * l / nz
+        xyz[nid(0, 0, l)] = (0.0, 0.0, z)
+        for k in range(1, n_rings + 1):
+            r = r_outer * k / n_rings
+            for s in range(n_sectors):
+                t = 2.0 * np.pi * s / n_sectors
+                xyz[nid(k, s, l)] = (r * np.cos(t), r * np.sin(t), z)
+    conn = []
+    for l in range(nz):
+        for k in range(n_rings):
+            for s in range(n_sectors):
+                conn.append([nid(k, s, l), nid(k + 1, s, l), nid(k + 1, s + 1, l), nid(k, s + 1, l),
+                             nid(k, s, l + 1), nid(k + 1, s, l + 1), nid(k + 1, s + 1, l + 1), nid(k, s + 1, l + 1)])
+    conn = np.asarray(conn, dtype=np.int32)
+    n_elem = conn.shape[0]
+    bottom = np.array(sorted({nid(k, s, 0) for k in range(n_rings + 1) for s in range(n_sectors)}), dtype=np.int32)
+    rim = np.array([nid(n_rings, s, nz) for s in range(n_sectors)], dtype=np.int32)
+    load_val = np.zeros((rim.size, 3))
+    load_val[:, 0] = 100.0 / rim.size
+    return Model(xyz=xyz, conn=conn, elem_type=np.full(n_elem, elem_type, dtype=np.uint8),
+                 elem_mat=np.zeros(n_elem, dtype=np.int32), elem_pid=np.ones(n_elem, dtype=np.int32),
+                 mat_E=np.array([E]), mat_nu=np.array([nu]), spc_node=bottom, spc_val=np.ones((bottom.size, 3)),
+                 load_node=rim, load_val=load_val, tolerance=tolerance, dims=(n_sectors, n_rings, nz))

@@ -258,3 +258,44 @@ def test_error_paths(solver):
     assert ei.value.code == native.E_STATE
     with pytest.raises(native.StanError):
         solver.SetDOF(np.zeros(m.n_nodes, np.int32))                      # not a permutation
+
+
+def test_unstructured_valence_and_degenerate_elements(solver, oracle):
+    """Polar disk: axis nodes touch 48 elements (96 incidence entries, 75 blocks per row) and the inner ring
+    is made of hexahedra collapsed to wedges (a node repeated in the connectivity)."""
+    import scipy.sparse.linalg as spl
+    from oracle import postprocess as PP
+    m = mesh.polar_disk(24, 3, 2, tolerance=1e-10)
+    ni, red, K = _assembled(solver, oracle, m)
+    assert np.array_equal(ni, oracle.assign_dof(m))
+    rp, col, val = solver.csr_upper()
+    orp, ocol, oval = K.arrays()
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
+    assert np.abs(val - oval).max() <= 1e-12 * np.abs(oval).max()
+    xr = np.random.default_rng(3).standard_normal(K.n)
+    y = solver.spmv(oracle.include_bc_dof(red, xr))[red != -1]
+    yo = oracle.sym_spmv(K, xr)
+    assert np.abs(y - yo).max() <= 1e-12 * np.abs(yo).max()
+    rep = solver.LinearSolver_CG(merit_check=0, IterMax=5000)
+    assert rep.terminationtype == 1
+    F = oracle.build_rhs(m, ni, red)
+    xs = spl.spsolve(K.to_scipy_full().tocsc(), F)
+    xg = solver.Exclude_BC_DOF()
+    assert np.linalg.norm(xg - xs) / np.linalg.norm(xs) < 1e-9
+    solver.Recovery_Stress()
+    U = solver.Include_BC_DOF()
+    strain, stress = solver.strain_stress()
+    es, ss = oracle.recover(m, ni, U)
+    assert np.abs(stress - ss).max() <= 1e-12 * np.abs(ss).max() and np.abs(strain - es).max() <= 1e-12 * np.abs(es).max()
+    cell, point, _ = solver.Load_Scalar()
+    ocell, opoint = PP.load_scalar(m, ni, U, strain, stress)
+    assert (np.abs(point - opoint) / (np.abs(opoint).max(axis=0, keepdims=True) + 1e-30)).max() < 2e-6
+    assert (np.abs(cell - ocell) / (np.abs(ocell).max(axis=(0, 2), keepdims=True) + 1e-30)).max() < 2e-6
+
+
+def test_row_wider_than_capacity_is_reported(solver):
+    m = mesh.polar_disk(40, 2, 2)                   # axis rows couple to 123 nodes > STAN_MAX_ROW_BLOCKS (96)
+    solver.SetModel(m); solver.AssignDOF()
+    with pytest.raises(native.StanError) as ei:
+        solver.ParallelAssembly_K()
+    assert ei.value.code == native.E_CAPACITY
