@@ -920,10 +920,14 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     launches++;
     STAN_TRY(reduce_tail(SC_INIT));
 
-    const int batch = rupd > 0 ? rupd : 10;
+    // One batch = two refresh periods, so the x / xalt roles are back where they started and every batch
+    // is the same launch sequence.  On one GPU without per-launch timing the batch is captured once into
+    // a CUDA graph and replayed: the loop is launch-bound on small systems (100k elements: 17 of 67 us
+    // per iteration were gaps between kernels).  Kernels enqueued after the state flags `done` return
+    // immediately, so replaying a whole batch past the end is harmless.
+    const int batch = 2 * (rupd > 0 ? rupd : 10);
     int k = 0;
-    bool done = false;
-    while (!done) {
+    auto enqueue_batch = [&]() -> int {
         for (int bi = 0; bi < batch; bi++) {
             k++;
             const int kk = k - off;
@@ -946,13 +950,44 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
             }
             k_direction<<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, h->d_p.p, st);
             launches++;
-            if (o->maxits > 0 && k >= o->maxits) break;
+        }
+        return STAN_OK;
+    };
+    static const bool graphs_on = !(getenv("STAN_GRAPH") && atoi(getenv("STAN_GRAPH")) == 0);
+    const bool use_graph = graphs_on && !multi && !timek;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    int64_t launches_per_batch = 0;
+    int spmv_per_batch = 0;
+    if (use_graph) {
+        const int64_t l0 = launches;
+        const int s0 = spmv_launches;
+        STAN_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_batch();
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc != STAN_OK) return rc;
+        STAN_CUDA(ce);
+        STAN_CUDA(cudaGraphInstantiate(&gexec, graph, 0));
+        launches_per_batch = launches - l0;
+        spmv_per_batch = spmv_launches - s0;
+        launches = l0; spmv_launches = s0;                  // counted per replay below
+    }
+    bool done = false;
+    while (!done) {
+        if (use_graph) {
+            STAN_CUDA(cudaGraphLaunch(gexec, s));
+            launches += launches_per_batch;
+            spmv_launches += spmv_per_batch;
+        } else {
+            STAN_TRY(enqueue_batch());
         }
         STAN_CUDA(cudaMemcpyAsync(hst, st, sizeof(CgState), cudaMemcpyDeviceToHost, s));
         STAN_CUDA(cudaStreamSynchronize(s));
         STAN_CUDA(cudaGetLastError());
         done = hst->done != 0;
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
     STAN_CUDA(cudaEventRecord(h->ev1, s));
     STAN_CUDA(cudaStreamSynchronize(s));
     float ms = 0.f;
