@@ -179,10 +179,16 @@ def run_ours(args):
     ni = s.AssignDOF()                                    # R0, host BFS (Database.cs:140-234); not in the step
     t_dof = time.perf_counter() - t0
 
+    call_wall = []                                        # host wall time of the three calls, per step
+
     def step(timek=1):
+        t0 = time.perf_counter()
         a = s.ParallelAssembly_K()
+        t1 = time.perf_counter()
         cg = s.LinearSolver_CG(merit_check=0, IterMax=args.cg_maxits, time_kernels=timek)
+        t2 = time.perf_counter()
         rc = s.Recovery_Stress()
+        call_wall.append((t1 - t0, t2 - t1, time.perf_counter() - t2))
         return a, cg, rc
 
     for _ in range(args.warmup):
@@ -200,10 +206,12 @@ def run_ours(args):
     wall_ms = (time.perf_counter() - t0) * 1e3
     launches = s.kernel_launches() - l0
     clocks = sampler.stop()
-    tmax = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    cw = np.array(call_wall[-args.steps:]).mean(axis=0) * 1e3
+    tmax = torch.tensor([dev_ms, wall_ms, cw[0], cw[1], cw[2]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms = float(tmax[0]) / args.steps, float(tmax[1]) / args.steps
+    call_ms = {"assemble": float(tmax[2]), "solve": float(tmax[3]), "recover": float(tmax[4])}
 
     # ---- end to end through the C ABI with host buffers (H2D + D2H inside the timed region) ----
     h2d = m.xyz.nbytes + m.conn.nbytes + m.elem_type.nbytes + m.elem_mat.nbytes + ni.nbytes + m.spc_node.nbytes \
@@ -245,7 +253,7 @@ def run_ours(args):
                       "cg_iter_gbs": cg.iter_bytes * cg.iterationscount / (cg.solve_ms * 1e-3) / 1e9,
                       "spmv_gbs": achieved, "spmv_ms": spmv_ms, "recovery_el_s": m.n_elem / (rc.recover_ms * 1e-3),
                       "recovery_gbs": rc.recover_bytes / (rc.recover_ms * 1e-3) / 1e9, "assign_dof_host_s": t_dof,
-                      "wall_ms_per_step": wall_ms},
+                      "wall_ms_per_step": wall_ms, "call_wall_ms_max_over_ranks": call_ms},
         "roofline": {"kernel": "k_spmv (block-row CSR SpMV + p.Ap)", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_launch": cg.spmv_bytes},

@@ -1,6 +1,7 @@
 // C ABI of libstan_b200.so (include/stan_b200.h): argument checking, call-order state machine,
 // host<->device copies at the boundary.  Orchestrates pattern.cu / assembly.cu / cg.cu / recovery.cu
 // in the order of Solver.SolverLinearStatics (/root/reference/src/STAN_Solver/Solver.cs:97-210).
+#include <chrono>
 #include <cmath>
 #include <thread>
 
@@ -133,6 +134,9 @@ int stan_destroy(stan_handle *h) {
     h->d_r.release(s); h->d_p.release(s); h->d_mv.release(s); h->d_partials.release(s); h->d_state.release(s);
     h->d_counter.release(s); h->d_ufull.release(s); h->d_strain.release(s); h->d_stress.release(s);
     h->d_cell.release(s); h->d_point.release(s); h->d_ke.release(s);
+    for (auto &sl : h->scratch) if (sl.p) cudaFreeAsync(sl.p, s);
+    if (h->h_state) cudaFreeHost(h->h_state);
+    for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
     cudaStreamSynchronize(s);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); cudaEventDestroy(h->ev2); cudaEventDestroy(h->ev3);
     for (int i = 0; i < 8; i++) if (h->user_ev[i]) cudaEventDestroy(h->user_ev[i]);
@@ -258,12 +262,23 @@ int stan_assemble(stan_handle *h, stan_assembly_stats *stats) {
     const int64_t launches0 = h->launches;
     h->assembled = h->solved = h->recovered = h->postprocessed = false;
     partition_rows(h);
+    static const bool trace = getenv("STAN_TRACE") != nullptr;      // host wall clock of the phases, to stderr
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double w0 = now();
     STAN_CUDA(cudaEventRecord(h->ev2, s));
     STAN_TRY(build_system_pattern(h));
+    const double w1 = now();
     STAN_TRY(comm_build_halo(h));
+    const double w2 = now();
     STAN_TRY(build_rhs(h));
+    const double w3 = now();
     STAN_CUDA(cudaEventRecord(h->ev0, s));
     STAN_TRY(run_assembly(h));
+    if (trace) {
+        cudaStreamSynchronize(s);
+        fprintf(stderr, "[stan rank %d] assemble: pattern %.1f ms, halo/p2p %.1f ms, rhs %.1f ms, kernels %.1f ms\n", h->rank,
+                w1 - w0, w2 - w1, w3 - w2, now() - w3);
+    }
     STAN_CUDA(cudaEventRecord(h->ev1, s));
     int32_t herr[4];
     STAN_CUDA(cudaMemcpyAsync(herr, h->d_err.p, sizeof herr, cudaMemcpyDeviceToHost, s));

@@ -492,16 +492,16 @@ static int run_assembly_two_kernel(stan_handle *h) {
     }
     // elements that touch an owned row: all of them on one GPU, a compacted list otherwise
     int64_t n_local = h->n_elem;
-    DevBuf<int32_t> g2l, lelem;
+    ScratchBuf<int32_t> g2l(&h->scratch[6]), lelem(&h->scratch[7]);
     if (h->world > 1) {
         int32_t n_inc = 0;
         STAN_CUDA(cudaMemcpyAsync(&n_inc, h->d_inc_ptr.p + nloc, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        DevBuf<int32_t> flag, pos;
+        ScratchBuf<int32_t> flag(&h->scratch[0]), pos(&h->scratch[1]);
         STAN_TRY(flag.alloc(h->n_elem + 1, s)); STAN_TRY(pos.alloc(h->n_elem + 1, s)); STAN_TRY(g2l.alloc(h->n_elem, s));
         STAN_CUDA(cudaMemsetAsync(flag.p, 0, (h->n_elem + 1) * sizeof(int32_t), s));
         STAN_CUDA(cudaStreamSynchronize(s));
         k_flag_local_elems<<<div_up(n_inc, 256), 256, 0, s>>>(n_inc, h->d_inc.p, flag.p);
-        STAN_TRY(device_exclusive_scan_i32(flag.p, pos.p, h->n_elem + 1, s));
+        STAN_TRY(device_exclusive_scan_i32(h, flag.p, pos.p, h->n_elem + 1, s));
         int32_t cnt = 0;
         STAN_CUDA(cudaMemcpyAsync(&cnt, pos.p + h->n_elem, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         STAN_CUDA(cudaStreamSynchronize(s));

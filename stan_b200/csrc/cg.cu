@@ -883,8 +883,8 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     init.restart = restart;
     init.comm = p2p ? comm_dev(h) : nullptr;
     init.red_seq = h->red_seq;              // flags in the peer windows persist across solves
-    CgState *hst = nullptr;
-    STAN_CUDA(cudaMallocHost((void **)&hst, sizeof(CgState)));
+    if (!h->h_state) STAN_CUDA(cudaMallocHost((void **)&h->h_state, sizeof(CgState)));
+    CgState *hst = h->h_state;
     *hst = init;
     STAN_CUDA(cudaMemcpyAsync(h->d_state.p, hst, sizeof(CgState), cudaMemcpyHostToDevice, s));
     CgState *st = h->d_state.p;
@@ -907,7 +907,14 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     auto spmv = [&](double *in, int slot, int step) -> int {
         if (multi) STAN_TRY(comm_halo_exchange(h, in, s, st));
         cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (timek) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+        if (timek) {                                       // events come from a grow-only pool kept on the handle
+            if (h->ev_pool.size() < evs.size() + 2) {
+                h->ev_pool.resize(evs.size() + 2, nullptr);
+                cudaEventCreate(&h->ev_pool[evs.size()]); cudaEventCreate(&h->ev_pool[evs.size() + 1]);
+            }
+            e0 = h->ev_pool[evs.size()]; e1 = h->ev_pool[evs.size() + 1];
+            cudaEventRecord(e0, s);
+        }
         launch_spmv(h, plan, true, nloc, in, h->d_mv.p, h->d_partials.p, h->d_counter.p + 2, st, slot, step, single, s);
         if (timek) { cudaEventRecord(e1, s); evs.push_back(e0); evs.push_back(e1); }
         launches++; spmv_launches++;
@@ -997,7 +1004,6 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
         // launches enqueued after the state flagged done return immediately; they are still counted
         cudaEventElapsedTime(&t, evs[i], evs[i + 1]);
         spmv_ms += t;
-        cudaEventDestroy(evs[i]); cudaEventDestroy(evs[i + 1]);
     }
     // accepted iterate: d_x unless an odd number of refreshes were accepted
     h->x_in_alt = hst->x_in_alt != 0;
@@ -1014,7 +1020,6 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     rep->iter_bytes = rep->spmv_bytes + 88 * n;
     rep->kernel_launches = launches;
     h->launches += launches;
-    cudaFreeHost(hst);
     if (p2p) {                                             // a peer never raised its flag (spin timed out)
         int32_t herr[8] = {0};
         STAN_CUDA(cudaMemcpy(herr, h->d_err.p, sizeof herr, cudaMemcpyDeviceToHost));

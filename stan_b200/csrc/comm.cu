@@ -247,7 +247,7 @@ static int p2p_setup(stan_handle *h) {
     for (int r = 0; r < W; r++) mine.recv_off[r] = c->recv_off[r];
     std::vector<Hello> all(W);
     {
-        DevBuf<Hello> dmine, dall;
+        ScratchBuf<Hello> dmine(&h->scratch[4]), dall(&h->scratch[5]);
         STAN_TRY(dmine.alloc(1, s)); STAN_TRY(dall.alloc(W, s));
         STAN_CUDA(cudaMemcpyAsync(dmine.p, &mine, sizeof mine, cudaMemcpyHostToDevice, s));
         STAN_NCCL(g_nccl.AllGather(dmine.p, dall.p, sizeof(Hello), 0 /* ncclInt8 */, c->comm, s));
@@ -272,7 +272,7 @@ static int p2p_setup(stan_handle *h) {
         if (m2.ok) m2.ok = cudaIpcGetMemHandle(&m2.handle, c->window) == cudaSuccess;
         cudaGetLastError();
         std::vector<Hello2> all2(W);
-        DevBuf<Hello2> dmine, dall;
+        ScratchBuf<Hello2> dmine(&h->scratch[4]), dall(&h->scratch[5]);
         STAN_TRY(dmine.alloc(1, s)); STAN_TRY(dall.alloc(W, s));
         STAN_CUDA(cudaMemcpyAsync(dmine.p, &m2, sizeof m2, cudaMemcpyHostToDevice, s));
         STAN_NCCL(g_nccl.AllGather(dmine.p, dall.p, sizeof(Hello2), 0, c->comm, s));
@@ -335,18 +335,16 @@ int comm_build_halo(stan_handle *h) {
     c->max_rows = 0;
     for (int r = 0; r < W; r++) c->max_rows = std::max(c->max_rows, c->bound[r + 1] - c->bound[r]);
 
-    DevBuf<int32_t> flag, slot;
+    ScratchBuf<int32_t> flag(&h->scratch[0]), slot(&h->scratch[1]);
     STAN_TRY(flag.alloc(nn + 1, s)); STAN_TRY(slot.alloc(nn + 1, s));
     STAN_CUDA(cudaMemsetAsync(flag.p, 0, (nn + 1) * sizeof(int32_t), s));
     k_mark_halo<<<div_up(h->n_blocks, 256), 256, 0, s>>>(h->n_blocks, h->d_bcol.p, h->row0, h->row1, flag.p);
     {
         size_t bytes = 0;
         STAN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag.p, slot.p, nn + 1, s));
-        void *tmp = nullptr;
-        STAN_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 1, s));
-        cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, bytes, flag.p, slot.p, nn + 1, s);
-        cudaFreeAsync(tmp, s);
-        STAN_CUDA(e);
+        ScratchBuf<unsigned char> tmp(&h->scratch[8]);
+        STAN_TRY(tmp.alloc(bytes ? bytes : 1, s));
+        STAN_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, flag.p, slot.p, nn + 1, s));
     }
     STAN_TRY(h->d_bcol_loc.alloc((size_t)h->n_blocks + 4, s));
     k_localize_cols<<<div_up(h->n_blocks, 256), 256, 0, s>>>(h->n_blocks, h->d_bcol.p, h->row0, h->row1, slot.p,
@@ -357,7 +355,7 @@ int comm_build_halo(stan_handle *h) {
     for (int r = 0; r <= W; r++)
         STAN_CUDA(cudaMemcpyAsync(&at[r], slot.p + c->bound[r], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     // send lists from the peer mask of the owned rows
-    DevBuf<uint32_t> mask; DevBuf<int64_t> dbound;
+    ScratchBuf<uint32_t> mask(&h->scratch[2]); ScratchBuf<int64_t> dbound(&h->scratch[3]);
     STAN_TRY(mask.alloc(nloc, s)); STAN_TRY(dbound.alloc(W + 1, s));
     STAN_CUDA(cudaMemcpyAsync(dbound.p, c->bound.data(), (W + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     k_peer_mask<<<div_up(nloc, 256), 256, 0, s>>>(nloc, h->d_brow_ptr.p, h->d_bcol.p, W, dbound.p, h->row0, h->row1,

@@ -59,6 +59,36 @@ struct DevBuf {
     }
 };
 
+// Grow-only scratch slots owned by the handle.  Temporaries of assemble/solve live here so that the
+// steady state performs no device allocation at all (one observed 600 ms stall in a stream-ordered
+// allocation in the middle of a run was enough reason).  Same interface as DevBuf; release() is a no-op.
+struct ScratchSlot { void *p = nullptr; size_t bytes = 0; };
+template <typename T>
+struct ScratchBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ScratchSlot *slot;
+    explicit ScratchBuf(ScratchSlot *s) : slot(s) {}
+    int alloc(size_t count, cudaStream_t s) {
+        const size_t need = (count ? count : 1) * sizeof(T);
+        if (need > slot->bytes) {
+            if (slot->p) cudaFreeAsync(slot->p, s);
+            const size_t cap = need + need / 4 + 256;
+            cudaError_t e = cudaMallocAsync(&slot->p, cap, s);
+            if (e != cudaSuccess) {
+                slot->p = nullptr; slot->bytes = 0;
+                set_error("cudaMallocAsync(%zu bytes): %s", cap, cudaGetErrorString(e));
+                return STAN_E_CUDA;
+            }
+            slot->bytes = cap;
+        }
+        p = (T *)slot->p;
+        n = count;
+        return STAN_OK;
+    }
+    void release(cudaStream_t) {}
+};
+
 // Peer-memory window of one rank (multi-GPU, comm.cu).  Every rank cudaMalloc's one window, the
 // ranks exchange CUDA IPC handles once per assemble, and from then on halo values and partial sums
 // travel as plain stores into the neighbour's window over NVLink — no collective library in the CG
@@ -114,6 +144,7 @@ struct stan_handle {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
     cudaEvent_t user_ev[8] = {};
+    std::vector<cudaEvent_t> ev_pool;       // per-launch timing events (time_kernels), reused across solves
     void *stage[2] = {nullptr, nullptr};   // pinned staging for large device-to-host results
     cudaEvent_t stage_ev[2] = {};
 
@@ -172,6 +203,8 @@ struct stan_handle {
     stan::DevBuf<float> d_cell, d_point;      // post-processing scalars: [elem][24][3], [node][24]
     bool postprocessed = false;
 
+    stan::ScratchSlot scratch[12];      // see ScratchBuf: 0-5 pattern/halo/assembly temporaries, 6-7 element maps, 8 scan
+    stan::CgState *h_state = nullptr;   // pinned mirror of the device CG state
     stan::Comm *comm = nullptr;
     int64_t launches = 0;
 };
@@ -184,7 +217,7 @@ int assign_dof_host(int64_t n_nodes, int64_t n_elem, const int32_t *conn, int32_
 // pattern.cu
 int build_system_pattern(stan_handle *h);
 int build_rhs(stan_handle *h);
-int device_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s);
+int device_exclusive_scan_i32(stan_handle *h, const int32_t *in, int32_t *out, int64_t n, cudaStream_t s);
 int export_csr_upper_size(stan_handle *h, int64_t *n, int64_t *nnz);
 int export_csr_upper(stan_handle *h, int64_t *rowptr, int32_t *col, double *val);
 

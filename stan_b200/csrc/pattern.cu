@@ -163,21 +163,19 @@ __global__ void k_upper_rows(int64_t nloc, int64_t row0, const int32_t *__restri
 }
 
 template <typename T>
-int exclusive_scan(const T *in, T *out, int64_t n, cudaStream_t s) {
+int exclusive_scan(stan_handle *h, const T *in, T *out, int64_t n, cudaStream_t s) {
     size_t bytes = 0;
     STAN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, s));
-    void *tmp = nullptr;
-    STAN_CUDA(cudaMallocAsync(&tmp, bytes ? bytes : 1, s));
-    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, bytes, in, out, n, s);
-    cudaFreeAsync(tmp, s);
-    STAN_CUDA(e);
+    ScratchBuf<unsigned char> tmp(&h->scratch[8]);
+    STAN_TRY(tmp.alloc(bytes ? bytes : 1, s));
+    STAN_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, n, s));
     return STAN_OK;
 }
 
 }  // namespace
 
-int device_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
-    return exclusive_scan(in, out, n, s);
+int device_exclusive_scan_i32(stan_handle *h, const int32_t *in, int32_t *out, int64_t n, cudaStream_t s) {
+    return exclusive_scan(h, in, out, n, s);
 }
 
 int build_system_pattern(stan_handle *h) {
@@ -193,11 +191,11 @@ int build_system_pattern(stan_handle *h) {
 
     // incidence of the owned rows
     STAN_TRY(h->d_inc_ptr.alloc(nloc + 1, s));
-    DevBuf<int32_t> cnt;
+    ScratchBuf<int32_t> cnt(&h->scratch[0]);
     STAN_TRY(cnt.alloc(nloc + 1, s));
     STAN_CUDA(cudaMemsetAsync(cnt.p, 0, (nloc + 1) * sizeof(int32_t), s));
     k_inc_count<<<div_up(8 * ne, T), T, 0, s>>>(8 * ne, h->d_conn.p, h->d_node_index.p, h->row0, nloc, cnt.p);
-    STAN_TRY(exclusive_scan(cnt.p, h->d_inc_ptr.p, nloc + 1, s));
+    STAN_TRY(exclusive_scan(h, cnt.p, h->d_inc_ptr.p, nloc + 1, s));
     int32_t n_inc = 0;
     STAN_CUDA(cudaMemcpyAsync(&n_inc, h->d_inc_ptr.p + nloc, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     STAN_CUDA(cudaStreamSynchronize(s));
@@ -211,7 +209,7 @@ int build_system_pattern(stan_handle *h) {
     STAN_CUDA(cudaMemsetAsync(cnt.p, 0, (nloc + 1) * sizeof(int32_t), s));
     k_row_neighbors<false><<<div_up(nloc, 128), 128, 0, s>>>(nloc, h->d_inc_ptr.p, h->d_inc.p, h->d_conn.p,
                                                              h->d_node_index.p, cnt.p, nullptr, nullptr, h->d_err.p);
-    STAN_TRY(exclusive_scan(cnt.p, h->d_brow_ptr.p, nloc + 1, s));
+    STAN_TRY(exclusive_scan(h, cnt.p, h->d_brow_ptr.p, nloc + 1, s));
     int32_t nblk = 0, herr[4];
     STAN_CUDA(cudaMemcpyAsync(&nblk, h->d_brow_ptr.p + nloc, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     STAN_CUDA(cudaMemcpyAsync(herr, h->d_err.p, sizeof herr, cudaMemcpyDeviceToHost, s));
@@ -238,7 +236,7 @@ int build_system_pattern(stan_handle *h) {
     STAN_CUDA(cudaMemsetAsync(h->d_fixed.p, 0, ndof, s));
     const int64_t nspc = (int64_t)h->h_spc_node.size();
     if (nspc) {
-        DevBuf<int32_t> dn; DevBuf<double> dv;
+        ScratchBuf<int32_t> dn(&h->scratch[2]); ScratchBuf<double> dv(&h->scratch[3]);
         STAN_TRY(dn.alloc(nspc, s)); STAN_TRY(dv.alloc(3 * nspc, s));
         STAN_CUDA(cudaMemcpyAsync(dn.p, h->h_spc_node.data(), nspc * sizeof(int32_t), cudaMemcpyHostToDevice, s));
         STAN_CUDA(cudaMemcpyAsync(dv.p, h->h_spc_val.data(), 3 * nspc * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -246,11 +244,11 @@ int build_system_pattern(stan_handle *h) {
         dn.release(s); dv.release(s);
     }
     {
-        DevBuf<int32_t> tmp;
+        ScratchBuf<int32_t> tmp(&h->scratch[1]);
         STAN_TRY(tmp.alloc(ndof + 1, s));
         STAN_CUDA(cudaMemsetAsync(tmp.p + ndof, 0, sizeof(int32_t), s));
         k_fixed_to_int<<<div_up(ndof, T), T, 0, s>>>(ndof, h->d_fixed.p, tmp.p);
-        STAN_TRY(exclusive_scan(tmp.p, h->d_red.p, ndof + 1, s));
+        STAN_TRY(exclusive_scan(h, tmp.p, h->d_red.p, ndof + 1, s));
         tmp.release(s);
         int32_t nfix = 0;
         STAN_CUDA(cudaMemcpyAsync(&nfix, h->d_red.p + ndof, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -286,7 +284,7 @@ int build_rhs(stan_handle *h) {
             if (it == slot.end()) { slot.emplace(dof, dofs.size()); dofs.push_back(dof); vals.push_back(0.0 + h->h_load_val[3 * i + d]); }
             else vals[it->second] += h->h_load_val[3 * i + d];
         }
-    DevBuf<int64_t> dd; DevBuf<double> dv;
+    ScratchBuf<int64_t> dd(&h->scratch[2]); ScratchBuf<double> dv(&h->scratch[3]);
     STAN_TRY(dd.alloc(dofs.size(), s)); STAN_TRY(dv.alloc(vals.size(), s));
     STAN_CUDA(cudaMemcpyAsync(dd.p, dofs.data(), dofs.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaMemcpyAsync(dv.p, vals.data(), vals.size() * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -308,7 +306,7 @@ static int upper_counts(stan_handle *h, DevBuf<int64_t> &rowptr, int64_t *n_out,
     STAN_CUDA(cudaMemsetAsync(cnt.p, 0, (n + 1) * sizeof(int64_t), s));
     k_upper_rows<false><<<div_up(3 * nloc, 128), 128, 0, s>>>(nloc, h->row0, h->d_brow_ptr.p, h->d_bcol.p, h->d_vals.p,
                                                               h->d_fixed.p, h->d_red.p, cnt.p, nullptr, nullptr, nullptr);
-    STAN_TRY(exclusive_scan(cnt.p, rowptr.p, n + 1, s));
+    STAN_TRY(exclusive_scan(h, cnt.p, rowptr.p, n + 1, s));
     int64_t nnz = 0;
     STAN_CUDA(cudaMemcpyAsync(&nnz, rowptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     STAN_CUDA(cudaStreamSynchronize(s));
