@@ -35,6 +35,7 @@ extern "C" {
 #define STAN_E_CAPACITY   -5  /* a node couples to more nodes than STAN_MAX_ROW_BLOCKS */
 #define STAN_E_DOFMAP     -6  /* AssignDOF failed: no start node / disconnected mesh (Database.cs:178-196, :218) */
 #define STAN_E_COMM       -7  /* NCCL / multi-GPU failure */
+#define STAN_E_NOMEM      -8  /* the direct solver's skyline does not fit the device */
 
 #define STAN_HEX8_G1 1        /* Element.Type "HEX8_G1", FE_Library.cs:63-89 */
 #define STAN_HEX8_G2 2        /* Element.Type "HEX8_G2", FE_Library.cs:91-131 */
@@ -92,6 +93,20 @@ typedef struct {
     int64_t kernel_launches;
 } stan_assembly_stats;
 
+/* What LinearSolver_Cholesky prints (SolverFunctions.cs:386-437) plus device figures. */
+typedef struct {
+    int32_t terminationtype;   /* sparsecholeskysolvesks: 1 = solved, -3 = not positive definite (U = 0) */
+    int32_t block;             /* edge of the dense blocks the skyline is stored in (64) */
+    int64_t n;                 /* rows factorised: nDOF, fixed DOFs kept as identity rows */
+    int64_t n_blocks;          /* dense blocks inside the block skyline */
+    int64_t skyline_bytes;     /* device bytes of the factor */
+    double  flops;             /* flops of the factorisation as executed (dense blocks) */
+    double  setup_ms;          /* envelope + CRS -> skyline (sparseconverttosks) */
+    double  factor_ms;         /* sparsecholeskyskyline */
+    double  solve_ms;          /* sparsecholeskysolvesks: two triangular solves */
+    int64_t kernel_launches;
+} stan_chol_report;
+
 typedef struct {
     double  recover_ms;
     int64_t recover_bytes;     /* algorithmic bytes */
@@ -125,6 +140,9 @@ int stan_set_loads(stan_handle *h, int64_t n, const int32_t *node, const double 
 int stan_assemble(stan_handle *h, stan_assembly_stats *stats);
 /* Fun.LinearSolver_CG(K, F, AnalysisLib) (Solver.cs:162, SolverFunctions.cs:270-330). */
 int stan_solve_cg(stan_handle *h, const stan_cg_options *opts, stan_cg_report *report);
+/* Fun.LinearSolver_Cholesky(K, F) (Solver.cs:163, SolverFunctions.cs:332-444): skyline U^T U
+ * factorisation and two triangular solves on one GPU; leaves U where stan_solve_cg leaves it. */
+int stan_solve_cholesky(stan_handle *h, stan_chol_report *report);
 /* Include_BC_DOF + dU_buffer + Elem.Recovery_Stress + Update_StrainStress
  * (Solver.cs:168-210, Element.cs:211-246, 257-267). */
 int stan_recover(stan_handle *h, stan_recovery_stats *stats);

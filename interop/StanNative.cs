@@ -42,6 +42,15 @@ namespace STAN_Solver
         }
 
         [StructLayout(LayoutKind.Sequential)]
+        internal struct CholReport
+        {
+            public int terminationtype, block;
+            public long n, n_blocks, skyline_bytes;
+            public double flops, setup_ms, factor_ms, solve_ms;
+            public long kernel_launches;
+        }
+
+        [StructLayout(LayoutKind.Sequential)]
         internal struct RecoveryStats { public double recover_ms; public long recover_bytes, kernel_launches; }
 
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern IntPtr stan_last_error();
@@ -54,6 +63,7 @@ namespace STAN_Solver
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_set_loads(IntPtr h, long n, int[] node, double[] fxyz);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_assemble(IntPtr h, out AssemblyStats st);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_solve_cg(IntPtr h, ref CgOptions o, out CgReport rep);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_solve_cholesky(IntPtr h, out CholReport rep);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_recover(IntPtr h, out RecoveryStats st);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_get_displacements(IntPtr h, double[] uFull);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_get_strain_stress(IntPtr h, double[] strain, double[] stress);
@@ -124,15 +134,28 @@ namespace STAN_Solver
                 StanNative.Check(StanNative.stan_assemble(h, out var a));
                 Console.WriteLine("          Done in " + (a.total_ms / 1000.0).ToString("F2") + "s");
 
-                Console.Write("   Solving linear system...   ");            // SolverFunctions.cs:273
-                var cg = new StanNative.CgOptions
+                if (DB.AnalysisLib.GetLinSolver() == "Cholesky")           // Solver.cs:163, SolverFunctions.cs:384-441
                 {
-                    epsf = DB.AnalysisLib.GetLinSolverTolerance(), maxits = DB.AnalysisLib.GetLinSolverMaxIter(),
-                    its_before_rupdate = 10, its_before_restart = 0, merit_check = 1
-                };
-                StanNative.Check(StanNative.stan_solve_cg(h, ref cg, out var rep));
-                Console.Write(rep.terminationtype == 1 || rep.terminationtype == 7 ? "  NORMAL " : "  ERROR ");   // :323-325
-                Console.WriteLine(" (type " + rep.terminationtype + ") in " + (rep.solve_ms / 1000.0).ToString("F2") + "s");
+                    Console.WriteLine("   Linear system K*U=F:");
+                    Console.Write("    - Cholesky decomposition:");
+                    StanNative.Check(StanNative.stan_solve_cholesky(h, out var ch));
+                    Console.WriteLine(ch.terminationtype > 0 ? "   Done" : "   ERROR");
+                    Console.WriteLine("    - Solving:                  " + (ch.terminationtype > 0 ? "NORMAL" : "ERROR") +
+                                      " termination (type " + ch.terminationtype + ")");
+                    Console.WriteLine("    Total time to solve K*U=F:  " + ((ch.setup_ms + ch.factor_ms + ch.solve_ms) / 1000.0).ToString("F2") + "s");
+                }
+                else
+                {
+                    Console.Write("   Solving linear system...   ");            // SolverFunctions.cs:273
+                    var cg = new StanNative.CgOptions
+                    {
+                        epsf = DB.AnalysisLib.GetLinSolverTolerance(), maxits = DB.AnalysisLib.GetLinSolverMaxIter(),
+                        its_before_rupdate = 10, its_before_restart = 0, merit_check = 1
+                    };
+                    StanNative.Check(StanNative.stan_solve_cg(h, ref cg, out var rep));
+                    Console.Write(rep.terminationtype == 1 || rep.terminationtype == 7 ? "  NORMAL " : "  ERROR ");   // :323-325
+                    Console.WriteLine(" (type " + rep.terminationtype + ") in " + (rep.solve_ms / 1000.0).ToString("F2") + "s");
+                }
 
                 Console.Write("   Stress recovery: ");                     // Solver.cs:183
                 StanNative.Check(StanNative.stan_recover(h, out _));

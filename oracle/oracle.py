@@ -191,6 +191,17 @@ def lincg(K: UpperCsr, b, opts: CgOpts):
     return x, rep
 
 
+def cholesky_skyline(K: UpperCsr, b):
+    """LinearSolver_Cholesky (SolverFunctions.cs:332-444): returns (x, terminationtype, envelope size)."""
+    b = _f64(b)
+    x = np.zeros(K.n)
+    env = C.c_int64(0)
+    fn = lib().stan_oracle_cholesky_skyline
+    fn.restype = C.c_int
+    tt = fn(C.c_void_p(K._h), _p(b), _p(x), C.byref(env))
+    return x, int(tt), int(env.value)
+
+
 def sym_spmv(K: UpperCsr, x):
     x = _f64(x)
     y = np.zeros(K.n)

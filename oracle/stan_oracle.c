@@ -694,6 +694,77 @@ done:
 OX void stan_oracle_sym_spmv(const oracle_csr *A, const double *x, double *y) { sym_spmv_upper(A, x, y); }
 
 /* ------------------------------------------------------------------------------------ */
+/* R3b: LinearSolver_Cholesky (SolverFunctions.cs:332-444): sparseconverttosks +           */
+/* sparsecholeskyskyline(isupper=true) + sparsecholeskysolvesks of alglib.net 3.16.0       */
+/* ------------------------------------------------------------------------------------ */
+
+/* Skyline (SKS) storage of the upper triangle: column j holds rows first[j]..j, where first[j]
+ * is the smallest row with a stored entry in that column (SolverFunctions.cs:385 converts the
+ * CRS matrix; fill-in stays inside this envelope).  Factorisation A = U^T U by the bordering
+ * scheme ALGLIB documents for sparsecholeskyskyline ("in-place ... best on low-profile
+ * matrices", quoted at SolverFunctions.cs:336-381): for column j, rows ascending,
+ *     u_ij = (a_ij - sum_{k=max(first[i],first[j])}^{i-1} u_ki u_kj) / u_ii,
+ *     u_jj = sqrt(a_jj - sum_k u_kj^2), and the routine reports failure when the radicand <= 0.
+ * The solve follows sparsecholeskysolvesks (SolverFunctions.cs:398-427): U^T y = b by column
+ * dot products, then U x = y by column sweeps from the last column; terminationtype 1 on
+ * success, -3 with x = 0 on failure.  Sum orders (k ascending, dot then subtract) are the
+ * published algorithm's natural ones; like the rest of the ALGLIB restatement they are unpinned. */
+OX int stan_oracle_cholesky_skyline(const oracle_csr *A, const double *b, double *x, int64_t *envelope_out) {
+    int64_t n = A->n;
+    int64_t *first = malloc((size_t)(n + 1) * sizeof(int64_t));
+    int64_t *cp = malloc((size_t)(n + 1) * sizeof(int64_t));
+    for (int64_t j = 0; j < n; j++) first[j] = j;
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t t = A->rowptr[i]; t < A->rowptr[i + 1]; t++) {
+            int64_t j = A->col[t];
+            if (j >= i && i < first[j]) first[j] = i;
+        }
+    cp[0] = 0;
+    for (int64_t j = 0; j < n; j++) cp[j + 1] = cp[j] + (j - first[j] + 1);
+    if (envelope_out) *envelope_out = cp[n];
+    double *S = calloc((size_t)cp[n] + 1, sizeof(double));
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t t = A->rowptr[i]; t < A->rowptr[i + 1]; t++) {
+            int64_t j = A->col[t];
+            if (j >= i) S[cp[j] + (i - first[j])] = A->val[t];
+        }
+#define SK(i, j) S[cp[j] + ((i) - first[j])]
+    int ok = 1;
+    for (int64_t j = 0; j < n && ok; j++) {
+        int64_t fj = first[j];
+        for (int64_t i = fj; i < j; i++) {
+            int64_t k0 = first[i] > fj ? first[i] : fj;
+            double v = 0.0;
+            for (int64_t k = k0; k < i; k++) v += SK(k, i) * SK(k, j);
+            SK(i, j) = (SK(i, j) - v) / SK(i, i);
+        }
+        double d = 0.0;
+        for (int64_t k = fj; k < j; k++) d += SK(k, j) * SK(k, j);
+        double r = SK(j, j) - d;
+        if (!(r > 0.0)) { ok = 0; break; }
+        SK(j, j) = sqrt(r);
+    }
+    if (!ok) {
+        for (int64_t i = 0; i < n; i++) x[i] = 0.0;
+        free(S); free(first); free(cp);
+        return -3;
+    }
+    for (int64_t j = 0; j < n; j++) {                     /* U^T y = b */
+        double v = 0.0;
+        for (int64_t k = first[j]; k < j; k++) v += SK(k, j) * x[k];
+        x[j] = (b[j] - v) / SK(j, j);
+    }
+    for (int64_t j = n - 1; j >= 0; j--) {                /* U x = y */
+        x[j] = x[j] / SK(j, j);
+        double xj = x[j];
+        for (int64_t k = first[j]; k < j; k++) x[k] -= SK(k, j) * xj;
+    }
+#undef SK
+    free(S); free(first); free(cp);
+    return 1;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* R4: Recovery_Stress + Update_StrainStress (Element.cs:211-246, 257-267)                  */
 /* ------------------------------------------------------------------------------------ */
 

@@ -327,9 +327,17 @@ int stan_solve_cg(stan_handle *h, const stan_cg_options *opts, stan_cg_report *r
     return solve_cg(h, opts, report);
 }
 
+int stan_solve_cholesky(stan_handle *h, stan_chol_report *report) {
+    STAN_TRY(check(h));
+    if (!h->assembled) { set_error("stan_solve_cholesky before stan_assemble"); return STAN_E_STATE; }
+    if (!report) { set_error("stan_solve_cholesky: null report"); return STAN_E_ARG; }
+    h->recovered = h->postprocessed = false;
+    return solve_cholesky(h, report);
+}
+
 int stan_recover(stan_handle *h, stan_recovery_stats *stats) {
     STAN_TRY(check(h));
-    if (!h->solved) { set_error("stan_recover before stan_solve_cg"); return STAN_E_STATE; }
+    if (!h->solved) { set_error("stan_recover before a solve"); return STAN_E_STATE; }
     return run_recovery(h, stats);
 }
 

@@ -1,0 +1,379 @@
+// LinearSolver_Cholesky on the device (reference: SolverFunctions.cs:332-444 — ALGLIB's
+// sparseconverttosks + sparsecholeskyskyline(isupper) + sparsecholeskysolvesks).
+//
+// The reference factorises the upper skyline in place, one scalar column at a time.  On the GPU the
+// same envelope is kept, but in dense 64x64 blocks: block column J stores block rows F[J]..J
+// contiguously ("block skyline"), F made non-decreasing so that block row K's stored blocks are the
+// contiguous range K..E[K].  Factorisation A = U^T U is right-looking over block rows:
+//     panel(K):   U_KK = chol(A_KK);  U_KJ = U_KK^-T A_KJ          for J in (K, E[K]]
+//     update(K):  A_IJ -= U_KI^T U_KJ                              for K < I <= J <= E[K]
+// which is FP64-FMA bound (n * bandwidth^2 flops), not HBM bound like the CG path.  The triangular
+// solves U^T y = b and U x = y walk the same blocks once each.  SPC-fixed DOFs stay in the system as
+// identity rows (as in the CG path), so eliminating them only adds exact zeros; the tail of the last
+// block is padded with identity rows.  Every sum has a fixed order, so results are reproducible.
+// Single GPU: a skyline that does not fit one device is beyond what a direct solver is for here.
+#include "common.cuh"
+
+namespace stan {
+
+namespace {
+
+constexpr int CB = 64;           // dense block edge (scalar DOFs)
+constexpr int CBB = CB * CB;     // doubles per block
+constexpr int ERR_NOT_SPD = 5;   // slot in d_err
+
+struct BandDev {
+    double *band;
+    const int32_t *F;            // first stored block row of block column J
+    const int64_t *pofs;         // blocks before block column J
+    __device__ __forceinline__ double *blk(int I, int J) const {
+        return band + (pofs[J] + (int64_t)(I - F[J])) * CBB;
+    }
+};
+
+// smallest column node of every block row == first row of the node's three skyline columns / 3
+__global__ void k_min_col(int64_t n_nodes, const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
+                          int32_t *__restrict__ minnb) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    int32_t m = (int32_t)i;
+    for (int s = brow_ptr[i]; s < brow_ptr[i + 1]; s++) m = min(m, bcol[s]);
+    minnb[i] = m;
+}
+
+// upper triangle of the assembled block rows -> block skyline; fixed DOFs become identity rows/columns
+__global__ void k_band_scatter(int64_t n_nodes, const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
+                               const double *__restrict__ vals, const uint8_t *__restrict__ fixed, BandDev B) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= 3 * n_nodes) return;
+    const int64_t i = t / 3;
+    const int a = (int)(t % 3);
+    const int64_t r = t;
+    const int s0 = brow_ptr[i], s1 = brow_ptr[i + 1], nb = s1 - s0;
+    const double *rowv = vals + 9 * (int64_t)s0 + (int64_t)a * 3 * nb;
+    const bool rfix = fixed[r] != 0;
+    const int I = (int)(r / CB), rr = (int)(r % CB);
+    for (int s = s0; s < s1; s++) {
+        const int64_t q = bcol[s];
+        for (int b = 0; b < 3; b++) {
+            const int64_t c = 3 * q + b;
+            if (c < r) continue;
+            double v = rowv[3 * (s - s0) + b];
+            if (rfix || fixed[c]) v = (c == r) ? 1.0 : 0.0;
+            const int J = (int)(c / CB);
+            B.blk(I, J)[rr * CB + (int)(c % CB)] = v;
+        }
+    }
+}
+
+__global__ void k_band_pad(int64_t n, int64_t npad, BandDev B) {
+    int64_t r = n + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= npad) return;
+    const int J = (int)(r / CB), rr = (int)(r % CB);
+    B.blk(J, J)[rr * CB + rr] = 1.0;
+}
+
+// ---- panel: diagonal block Cholesky + row of triangular solves -------------------------------
+// 256 threads.  Every CTA factorises the 64x64 diagonal block in shared memory (identical arithmetic,
+// so identical bits; it is cheaper than a second launch per block row), CTA 0 stores it, and each
+// 64-thread quarter then solves U_KK^T X = A_KJ for one block J with a column of X per thread held
+// in registers (no barriers in the 2016-FMA substitution; U_KK reads are shared-memory broadcasts).
+constexpr int PANEL_TILES = 4;
+__global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, int *__restrict__ err) {
+    __shared__ double D[CBB];
+    __shared__ double dg[CB];
+    const int tid = threadIdx.x;
+    double *gkk = B.blk(K, K);
+    for (int i = tid; i < CBB; i += 256) D[i] = gkk[i];
+    __syncthreads();
+    const int c = tid & 63, rq = tid >> 6;
+    for (int j = 0; j < CB; j++) {
+        double djj = D[j * CB + j];
+        if (!(djj > 0.0)) {                         // sparsecholeskyskyline returns false here
+            if (tid == 0 && blockIdx.x == 0) atomicOr(err + ERR_NOT_SPD, 1);
+            djj = 1.0;
+        }
+        const double sj = sqrt(djj);
+        if (tid < CB && tid > j) D[j * CB + tid] = D[j * CB + tid] / sj;
+        if (tid == j) dg[j] = sj;
+        __syncthreads();
+        const double ujc = D[j * CB + c];
+        for (int r = j + 1 + rq; r <= c; r += 4) D[r * CB + c] -= D[j * CB + r] * ujc;
+        __syncthreads();
+    }
+    if (tid < CB) D[tid * CB + tid] = dg[tid];
+    __syncthreads();
+    if (blockIdx.x == 0)
+        for (int i = tid; i < CBB; i += 256)
+            if ((i >> 6) <= (i & 63)) gkk[i] = D[i];
+
+    const int jt = blockIdx.x * PANEL_TILES + rq;
+    if (jt >= m) return;
+    double *g = B.blk(K, K + 1 + jt);
+    double t[CB];
+#pragma unroll
+    for (int r = 0; r < CB; r++) t[r] = g[r * CB + c];
+#pragma unroll
+    for (int r = 0; r < CB; r++) {
+        t[r] = t[r] / D[r * CB + r];
+#pragma unroll
+        for (int r2 = r + 1; r2 < CB; r2++) t[r2] -= D[r * CB + r2] * t[r];
+    }
+#pragma unroll
+    for (int r = 0; r < CB; r++) g[r * CB + c] = t[r];
+}
+
+// ---- trailing update: C_IJ -= U_KI^T U_KJ ----------------------------------------------------
+// One 64x64 block per CTA, 128 threads, 8x4 accumulators per thread: per k a thread reads 8 values
+// of U_KI (two addresses per warp: broadcast) and 2+2 of U_KJ (conflict-free 16-byte lanes), 32 FMAs.
+__global__ void __launch_bounds__(128) k_chol_update(BandDev B, int K) {
+    const int a = blockIdx.x, b = blockIdx.y;
+    if (a > b) return;
+    extern __shared__ __align__(16) double sm[];
+    double *As = sm, *Bs = sm + CBB;
+    const int tid = threadIdx.x;
+    const int I = K + 1 + a, J = K + 1 + b;
+    {
+        const double2 *ga = reinterpret_cast<const double2 *>(B.blk(K, I));
+        const double2 *gb = reinterpret_cast<const double2 *>(B.blk(K, J));
+        double2 *sa = reinterpret_cast<double2 *>(As), *sb = reinterpret_cast<double2 *>(Bs);
+#pragma unroll 8
+        for (int i = tid; i < CBB / 2; i += 128) { sa[i] = ga[i]; sb[i] = gb[i]; }
+    }
+    __syncthreads();
+    const int ty = tid >> 4, tx = tid & 15;
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < CB; k++) {
+        double av[8], bv[4];
+        const double2 *pa = reinterpret_cast<const double2 *>(As + k * CB + ty * 8);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { double2 v = pa[i]; av[2 * i] = v.x; av[2 * i + 1] = v.y; }
+        const double2 b0 = *reinterpret_cast<const double2 *>(Bs + k * CB + 2 * tx);
+        const double2 b1 = *reinterpret_cast<const double2 *>(Bs + k * CB + 32 + 2 * tx);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b1.x; bv[3] = b1.y;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] += av[i] * bv[j];
+    }
+    double *gc = B.blk(I, J);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        double2 *p0 = reinterpret_cast<double2 *>(gc + (ty * 8 + i) * CB + 2 * tx);
+        double2 *p1 = reinterpret_cast<double2 *>(gc + (ty * 8 + i) * CB + 32 + 2 * tx);
+        double2 c0 = *p0, c1 = *p1;
+        c0.x -= acc[i][0]; c0.y -= acc[i][1]; c1.x -= acc[i][2]; c1.y -= acc[i][3];
+        *p0 = c0; *p1 = c1;
+    }
+}
+
+// ---- U^T y = b, block row K: y_K = U_KK^-T w_K, then w_J -= U_KJ^T y_K for J in (K, E[K]] -------
+__global__ void __launch_bounds__(256) k_chol_fwd(BandDev B, int K, int m, double *__restrict__ w,
+                                                  double *__restrict__ y) {
+    __shared__ double D[CBB];
+    __shared__ double ys[CB];
+    __shared__ double part[4][CB];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const double *gkk = B.blk(K, K);
+    for (int i = tid; i < CBB; i += 256) D[i] = gkk[i];
+    if (tid < CB) ys[tid] = w[(int64_t)K * CB + tid];
+    __syncthreads();
+    if (tid < 32) {
+        double v0 = ys[lane], v1 = ys[lane + 32];
+        for (int r = 0; r < CB; r++) {
+            double yr = (r < 32) ? __shfl_sync(0xffffffffu, v0, r) : __shfl_sync(0xffffffffu, v1, r - 32);
+            yr = yr / D[r * CB + r];
+            if (lane == (r & 31)) { if (r < 32) v0 = yr; else v1 = yr; }
+            if (lane > r) v0 -= D[r * CB + lane] * yr;
+            if (lane + 32 > r) v1 -= D[r * CB + lane + 32] * yr;
+        }
+        ys[lane] = v0; ys[lane + 32] = v1;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid < CB) y[(int64_t)K * CB + tid] = ys[tid];
+    if ((int)blockIdx.x >= m) return;
+    const int J = K + 1 + blockIdx.x;
+    const double *g = B.blk(K, J);
+    const int c = tid & 63, q = tid >> 6;
+    double p = 0.0;
+#pragma unroll 4
+    for (int r = q * 16; r < q * 16 + 16; r++) p += g[r * CB + c] * ys[r];
+    part[q][c] = p;
+    __syncthreads();
+    if (q == 0) w[(int64_t)J * CB + c] -= ((part[0][c] + part[1][c]) + part[2][c]) + part[3][c];
+}
+
+// ---- U x = y, block column J (descending): x_J = U_JJ^-1 y_J, then y_I -= U_IJ x_J for I in [F[J], J) ----
+__global__ void __launch_bounds__(256) k_chol_bwd(BandDev B, int J, int cnt, double *__restrict__ y,
+                                                  double *__restrict__ x) {
+    __shared__ double D[CB * (CB + 1)];
+    __shared__ double xs[CB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double *gjj = B.blk(J, J);
+    for (int i = tid; i < CBB; i += 256) D[(i >> 6) * (CB + 1) + (i & 63)] = gjj[i];
+    if (tid < CB) xs[tid] = y[(int64_t)J * CB + tid];
+    __syncthreads();
+    if (tid < 32) {
+        double v0 = xs[lane], v1 = xs[lane + 32];
+        for (int c = CB - 1; c >= 0; c--) {
+            double xc = (c < 32) ? __shfl_sync(0xffffffffu, v0, c) : __shfl_sync(0xffffffffu, v1, c - 32);
+            xc = xc / D[c * (CB + 1) + c];
+            if (lane == (c & 31)) { if (c < 32) v0 = xc; else v1 = xc; }
+            if (lane < c) v0 -= D[lane * (CB + 1) + c] * xc;
+            if (lane + 32 < c) v1 -= D[(lane + 32) * (CB + 1) + c] * xc;
+        }
+        xs[lane] = v0; xs[lane + 32] = v1;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid < CB) x[(int64_t)J * CB + tid] = xs[tid];
+    if ((int)blockIdx.x >= cnt) return;
+    const int I = B.F[J] + blockIdx.x;
+    const double *g = B.blk(I, J);
+    for (int r = warp * 8; r < warp * 8 + 8; r++) {
+        double p = g[r * CB + lane] * xs[lane] + g[r * CB + lane + 32] * xs[lane + 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (lane == 0) y[(int64_t)I * CB + r] -= p;
+    }
+}
+
+}  // namespace
+
+int solve_cholesky(stan_handle *h, stan_chol_report *rep) {
+    if (!h->assembled) { set_error("stan_solve_cholesky: assemble first"); return STAN_E_STATE; }
+    if (h->world != 1) { set_error("stan_solve_cholesky is single-GPU only (the skyline is not partitioned)"); return STAN_E_STATE; }
+    cudaStream_t s = h->stream;
+    const int64_t nn = h->n_nodes, n = 3 * nn;
+    const int64_t nbk = (n + CB - 1) / CB, npad = nbk * CB;
+    if (nbk > 0x7fffffff / 2) { set_error("stan_solve_cholesky: too many rows"); return STAN_E_ARG; }
+    memset(rep, 0, sizeof *rep);
+    STAN_CUDA(cudaEventRecord(h->ev0, s));
+
+    // ---- block envelope (host: nbk integers) ----
+    DevBuf<int32_t> d_min;
+    STAN_TRY(d_min.alloc(nn, s));
+    k_min_col<<<div_up(nn, 256), 256, 0, s>>>(nn, h->d_brow_ptr.p, h->d_bcol.p, d_min.p);
+    std::vector<int32_t> minnb(nn);
+    STAN_CUDA(cudaMemcpyAsync(minnb.data(), d_min.p, nn * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    d_min.release(s);
+    std::vector<int32_t> F(nbk), E(nbk);
+    std::vector<int64_t> pofs(nbk + 1);
+    for (int64_t J = 0; J < nbk; J++) {
+        int64_t f = J;
+        const int64_t q0 = (J * CB) / 3, q1 = std::min(nn - 1, (J * CB + CB - 1) / 3);
+        for (int64_t q = q0; q <= q1; q++) f = std::min<int64_t>(f, (3 * (int64_t)minnb[q]) / CB);
+        F[J] = (int32_t)f;
+    }
+    for (int64_t J = nbk - 2; J >= 0; J--) F[J] = std::min(F[J], F[J + 1]);
+    pofs[0] = 0;
+    for (int64_t J = 0; J < nbk; J++) pofs[J + 1] = pofs[J] + (J - F[J] + 1);
+    {
+        int64_t J = 0;
+        for (int64_t K = 0; K < nbk; K++) {
+            if (J < K) J = K;
+            while (J + 1 < nbk && F[J + 1] <= K) J++;
+            E[K] = (int32_t)J;
+        }
+    }
+    const int64_t total_blocks = pofs[nbk];
+    const double band_bytes = (double)total_blocks * CBB * sizeof(double);
+    size_t mem_free = 0, mem_total = 0;
+    STAN_CUDA(cudaMemGetInfo(&mem_free, &mem_total));
+    if (band_bytes > 0.95 * (double)mem_total) {
+        set_error("stan_solve_cholesky: the skyline needs %.1f GB (%lld blocks of 64x64), the device has %.1f GB; use CG",
+                  band_bytes / 1e9, (long long)total_blocks, mem_total / 1e9);
+        return STAN_E_NOMEM;
+    }
+    DevBuf<double> band, w, y, x;
+    DevBuf<int32_t> dF;
+    DevBuf<int64_t> dP;
+    auto free_all = [&]() { band.release(s); w.release(s); y.release(s); x.release(s); dF.release(s); dP.release(s); };
+    if (band.alloc((size_t)total_blocks * CBB, s) != STAN_OK) {
+        free_all();
+        set_error("stan_solve_cholesky: cannot allocate the %.1f GB skyline; use CG", band_bytes / 1e9);
+        return STAN_E_NOMEM;
+    }
+    STAN_TRY(w.alloc(npad, s)); STAN_TRY(y.alloc(npad, s)); STAN_TRY(x.alloc(npad, s));
+    STAN_TRY(dF.alloc(nbk, s)); STAN_TRY(dP.alloc(nbk + 1, s));
+    STAN_CUDA(cudaMemcpyAsync(dF.p, F.data(), nbk * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaMemcpyAsync(dP.p, pofs.data(), (nbk + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    STAN_CUDA(cudaMemsetAsync(band.p, 0, (size_t)total_blocks * CBB * sizeof(double), s));
+    STAN_CUDA(cudaMemsetAsync(h->d_err.p + ERR_NOT_SPD, 0, sizeof(int32_t), s));
+    BandDev B{band.p, dF.p, dP.p};
+    k_band_scatter<<<div_up(n, 128), 128, 0, s>>>(nn, h->d_brow_ptr.p, h->d_bcol.p, h->d_vals.p, h->d_fixed.p, B);
+    if (npad > n) k_band_pad<<<1, CB, 0, s>>>(n, npad, B);
+    STAN_CUDA(cudaMemsetAsync(w.p, 0, npad * sizeof(double), s));
+    STAN_CUDA(cudaMemcpyAsync(w.p, h->d_b.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    int64_t launches = 3;
+
+    // ---- factorisation ----
+    static bool attr_set = false;
+    if (!attr_set) {
+        STAN_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CBB * (int)sizeof(double)));
+        attr_set = true;
+    }
+    STAN_CUDA(cudaEventRecord(h->ev1, s));
+    double flops = 0.0;
+    const double b3 = (double)CB * CB * CB;
+    for (int64_t K = 0; K < nbk; K++) {
+        const int m = E[K] - (int)K;
+        k_chol_panel<<<std::max(1, div_up(m, PANEL_TILES)), 256, 0, s>>>(B, (int)K, m, h->d_err.p);
+        launches++;
+        flops += b3 / 3 + (double)m * b3;
+        if (m > 0) {
+            k_chol_update<<<dim3(m, m), 128, 2 * CBB * sizeof(double), s>>>(B, (int)K);
+            launches++;
+            flops += (double)m * (m + 1) * b3;      // m(m+1)/2 blocks x 2*64^3
+        }
+    }
+    STAN_CUDA(cudaEventRecord(h->ev2, s));
+
+    // ---- triangular solves ----
+    for (int64_t K = 0; K < nbk; K++) {
+        const int m = E[K] - (int)K;
+        k_chol_fwd<<<std::max(1, m), 256, 0, s>>>(B, (int)K, m, w.p, y.p);
+    }
+    for (int64_t J = nbk - 1; J >= 0; J--) {
+        const int cnt = (int)J - F[J];
+        k_chol_bwd<<<std::max(1, cnt), 256, 0, s>>>(B, (int)J, cnt, y.p, x.p);
+    }
+    launches += 2 * nbk;
+    STAN_CUDA(cudaEventRecord(h->ev3, s));
+    STAN_CUDA(cudaGetLastError());
+
+    STAN_TRY(h->d_x.alloc(n, s));
+    int32_t herr[8] = {0};
+    STAN_CUDA(cudaMemcpyAsync(herr, h->d_err.p, sizeof herr, cudaMemcpyDeviceToHost, s));
+    STAN_CUDA(cudaStreamSynchronize(s));
+    const bool spd = herr[ERR_NOT_SPD] == 0;
+    if (spd) STAN_CUDA(cudaMemcpyAsync(h->d_x.p, x.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    else     STAN_CUDA(cudaMemsetAsync(h->d_x.p, 0, n * sizeof(double), s));   // "filled by zeros" (SolverFunctions.cs:420)
+    STAN_CUDA(cudaStreamSynchronize(s));
+    float t01 = 0, t12 = 0, t23 = 0;
+    cudaEventElapsedTime(&t01, h->ev0, h->ev1);
+    cudaEventElapsedTime(&t12, h->ev1, h->ev2);
+    cudaEventElapsedTime(&t23, h->ev2, h->ev3);
+    free_all();
+    h->x_in_alt = false;
+    h->solved = true;
+    h->launches += launches;
+    rep->terminationtype = spd ? 1 : -3;
+    rep->block = CB;
+    rep->n = n;
+    rep->n_blocks = total_blocks;
+    rep->skyline_bytes = (int64_t)band_bytes;
+    rep->flops = flops;
+    rep->setup_ms = t01;
+    rep->factor_ms = t12;
+    rep->solve_ms = t23;
+    rep->kernel_launches = launches;
+    return STAN_OK;
+}
+
+}  // namespace stan

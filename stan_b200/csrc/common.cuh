@@ -234,6 +234,9 @@ int time_spmv(stan_handle *h, int reps, double *ms, int64_t *bytes);
 int64_t spmv_algorithmic_bytes(const stan_handle *h);
 int scatter_solution(stan_handle *h);
 
+// cholesky.cu
+int solve_cholesky(stan_handle *h, stan_chol_report *rep);
+
 // recovery.cu
 int run_recovery(stan_handle *h, stan_recovery_stats *st);
 

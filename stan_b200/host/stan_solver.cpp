@@ -131,7 +131,11 @@ int linear_statics(stdb::Database &db, int device, bool strict) {
     stan_cg_report rep;
     stan_recovery_stats rs;
     stan_cg_options cg;
+    stan_chol_report chol;
     memset(&cg, 0, sizeof cg);
+    memset(&rep, 0, sizeof rep);
+    memset(&chol, 0, sizeof chol);
+    const bool cholesky = db.analysis.present && db.analysis.linsolver == "Cholesky";   // Solver.cs:162-163
     do {
         if (stan_set_mesh(h, nn, xyz.data(), ne, conn.data(), etype.data(), emat.data())) { rc = fail("stan_set_mesh"); break; }
         if (stan_set_materials(h, (int32_t)E.size(), E.data(), nu.data())) { rc = fail("stan_set_materials"); break; }
@@ -149,16 +153,26 @@ int linear_statics(stdb::Database &db, int device, bool strict) {
         if (stan_assemble(h, &as)) { rc = fail("stan_assemble"); break; }
         printf("          Done in %.2fs\n", as.total_ms / 1000.0);   // :177
 
-        printf("   Solving linear system...   ");                 // :273
-        fflush(stdout);
-        cg.epsf = db.analysis.present ? db.analysis.tolerance : 1.0e-6;   // Analysis defaults, Analysis.cs:17-20
-        cg.maxits = db.analysis.present ? db.analysis.itermax : 0;
-        cg.its_before_rupdate = 10;
-        cg.merit_check = strict ? 0 : 1;
-        if (strict && cg.maxits == 0) cg.maxits = 100000;
-        if (stan_solve_cg(h, &cg, &rep)) { rc = fail("stan_solve_cg"); break; }
-        printf(rep.terminationtype == 1 || rep.terminationtype == 7 ? "  NORMAL " : "  ERROR ");   // :323-325
-        printf(" (type %d) in %.2fs\n", rep.terminationtype, rep.solve_ms / 1000.0);
+        if (cholesky) {                                           // SolverFunctions.cs:384-441
+            printf("   Linear system K*U=F:\n    - Cholesky decomposition:");
+            fflush(stdout);
+            if (stan_solve_cholesky(h, &chol)) { rc = fail("stan_solve_cholesky"); break; }
+            printf(chol.terminationtype > 0 ? "   Done\n" : "   ERROR\n");
+            printf("    - Solving:                  %s termination (type %d)\n", chol.terminationtype > 0 ? "NORMAL" : "ERROR",
+                   chol.terminationtype);
+            printf("    Total time to solve K*U=F:  %.2fs\n", (chol.setup_ms + chol.factor_ms + chol.solve_ms) / 1000.0);
+        } else {
+            printf("   Solving linear system...   ");             // :273
+            fflush(stdout);
+            cg.epsf = db.analysis.present ? db.analysis.tolerance : 1.0e-6;   // Analysis defaults, Analysis.cs:17-20
+            cg.maxits = db.analysis.present ? db.analysis.itermax : 0;
+            cg.its_before_rupdate = 10;
+            cg.merit_check = strict ? 0 : 1;
+            if (strict && cg.maxits == 0) cg.maxits = 100000;
+            if (stan_solve_cg(h, &cg, &rep)) { rc = fail("stan_solve_cg"); break; }
+            printf(rep.terminationtype == 1 || rep.terminationtype == 7 ? "  NORMAL " : "  ERROR ");   // :323-325
+            printf(" (type %d) in %.2fs\n", rep.terminationtype, rep.solve_ms / 1000.0);
+        }
 
         printf("   Stress recovery: ");                           // Solver.cs:183
         fflush(stdout);
@@ -196,9 +210,14 @@ int linear_statics(stdb::Database &db, int device, bool strict) {
     db.analysis.present = true;
     db.analysis.result_stepno = 1;                                // Solver.cs:56
     printf("\n%s\n  Total CPU time: %.2f s\n%s\n", SEP, now_s() - t_start, SEP);   // Solver.cs:213-216
-    printf("   CG iterations: %d, ||r||/||b|| = %.3e, SpMV launches: %d, assembly kernel %.2f ms, recovery %.2f ms\n",
-           rep.iterationscount, rep.bnorm > 0 ? std::sqrt(rep.r2) / rep.bnorm : 0.0, rep.spmv_launches, as.assembly_ms,
-           rs.recover_ms);
+    if (cholesky)
+        printf("   Cholesky: skyline %.2f GB in %lld blocks of 64x64, factor %.2f ms (%.2f TFLOP/s), solves %.2f ms, "
+               "assembly kernel %.2f ms, recovery %.2f ms\n", chol.skyline_bytes / 1e9, (long long)chol.n_blocks, chol.factor_ms,
+               chol.factor_ms > 0 ? chol.flops / chol.factor_ms / 1e9 : 0.0, chol.solve_ms, as.assembly_ms, rs.recover_ms);
+    else
+        printf("   CG iterations: %d, ||r||/||b|| = %.3e, SpMV launches: %d, assembly kernel %.2f ms, recovery %.2f ms\n",
+               rep.iterationscount, rep.bnorm > 0 ? std::sqrt(rep.r2) / rep.bnorm : 0.0, rep.spmv_launches, as.assembly_ms,
+               rs.recover_ms);
     return 0;
 }
 
@@ -249,8 +268,9 @@ int main(int argc, char **argv) {
         fprintf(stderr, "stan_solver: analysis type '%s' is not on the native path (only Linear_Statics)\n", db.analysis.type.c_str());
         return 3;
     }
-    if (db.analysis.present && !db.analysis.linsolver.empty() && db.analysis.linsolver != "CG") {
-        fprintf(stderr, "stan_solver: linear solver '%s' is not on the native path (only CG)\n", db.analysis.linsolver.c_str());
+    if (db.analysis.present && !db.analysis.linsolver.empty() && db.analysis.linsolver != "CG" &&
+        db.analysis.linsolver != "Cholesky") {                    // Solver.cs:162-164 also knows "LU"
+        fprintf(stderr, "stan_solver: linear solver '%s' is not on the native path (CG and Cholesky are)\n", db.analysis.linsolver.c_str());
         return 3;
     }
     int rc = linear_statics(db, device, strict);

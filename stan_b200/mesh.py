@@ -45,6 +45,7 @@ class Model:
     load_val: np.ndarray       # (n_load, 3) float64
     tolerance: float = 1.0e-8  # Analysis.LinSolverTolerance
     max_iter: int = 0          # Analysis.LinSolverIterMax
+    lin_solver: str = "CG"     # Analysis.LinSolver: "CG" | "Cholesky" (Solver.cs:162-164)
     dims: tuple = field(default=(0, 0, 0))
 
     @property

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libstan_b200.so")
 
-OK, E_ARG, E_CUDA, E_SINGULAR, E_STATE, E_CAPACITY, E_DOFMAP, E_COMM = 0, -1, -2, -3, -4, -5, -6, -7
+OK, E_ARG, E_CUDA, E_SINGULAR, E_STATE, E_CAPACITY, E_DOFMAP, E_COMM, E_NOMEM = 0, -1, -2, -3, -4, -5, -6, -7, -8
 
 
 class StanError(RuntimeError):
@@ -44,6 +44,12 @@ class AssemblyStats(C.Structure):
                 ("total_ms", C.c_double), ("kernel_launches", C.c_int64)]
 
 
+class CholReport(C.Structure):
+    _fields_ = [("terminationtype", C.c_int32), ("block", C.c_int32), ("n", C.c_int64), ("n_blocks", C.c_int64),
+                ("skyline_bytes", C.c_int64), ("flops", C.c_double), ("setup_ms", C.c_double),
+                ("factor_ms", C.c_double), ("solve_ms", C.c_double), ("kernel_launches", C.c_int64)]
+
+
 class RecoveryStats(C.Structure):
     _fields_ = [("recover_ms", C.c_double), ("recover_bytes", C.c_int64), ("kernel_launches", C.c_int64)]
 
@@ -63,6 +69,7 @@ SYMBOLS = {
     "stan_set_loads": (C.c_int, [_P, _I64, _P, _P]),
     "stan_assemble": (C.c_int, [_P, C.POINTER(AssemblyStats)]),
     "stan_solve_cg": (C.c_int, [_P, C.POINTER(CgOptions), C.POINTER(CgReport)]),
+    "stan_solve_cholesky": (C.c_int, [_P, C.POINTER(CholReport)]),
     "stan_recover": (C.c_int, [_P, C.POINTER(RecoveryStats)]),
     "stan_get_displacements": (C.c_int, [_P, _P]),
     "stan_get_strain_stress": (C.c_int, [_P, _P, _P]),

@@ -106,6 +106,12 @@ class Solver:
         native.check(self._lib.stan_solve_cg(self._h, C.byref(o), C.byref(rep)))
         return rep
 
+    def LinearSolver_Cholesky(self) -> native.CholReport:
+        """Fun.LinearSolver_Cholesky(K, F) (SolverFunctions.cs:332-444): skyline U^T U on one GPU."""
+        rep = native.CholReport()
+        native.check(self._lib.stan_solve_cholesky(self._h, C.byref(rep)))
+        return rep
+
     def Recovery_Stress(self) -> native.RecoveryStats:
         st = native.RecoveryStats()
         native.check(self._lib.stan_recover(self._h, C.byref(st)))
@@ -214,7 +220,12 @@ class Solver:
         else:
             self.SetDOF(node_index)
         a = self.ParallelAssembly_K()
-        cg = self.LinearSolver_CG(merit_check=merit_check, time_kernels=time_kernels)
+        if m.lin_solver == "CG":                                   # Solver.cs:162-164
+            cg = self.LinearSolver_CG(merit_check=merit_check, time_kernels=time_kernels)
+        elif m.lin_solver == "Cholesky":
+            cg = self.LinearSolver_Cholesky()
+        else:
+            raise ValueError(f"LinSolver {m.lin_solver!r} is not provided (CG and Cholesky are)")
         rec = self.Recovery_Stress()
         if not fetch:
             return LinearStaticsResult(self.node_index, None, None, None, None, a, cg, rec)

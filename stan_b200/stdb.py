@@ -377,7 +377,7 @@ def from_model(m: Model, *, first_id: int = 1) -> Database:
                              nodal=[(int(n) + first_id, MatrixST(list(map(float, v)), 3, 1)) for n, v in zip(m.load_node, m.load_val)])
     db.bcs = [(1, spc), (2, load)]
     db.ndof = m.n_dof
-    db.analysis = Analysis(tolerance=float(m.tolerance), itermax=int(m.max_iter), incnumb=1)
+    db.analysis = Analysis(linsolver=m.lin_solver, tolerance=float(m.tolerance), itermax=int(m.max_iter), incnumb=1)
     return db
 
 

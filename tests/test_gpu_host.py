@@ -39,3 +39,31 @@ def test_stan_solver_cli_roundtrip_against_oracle(oracle, tmp_path):
     assert r2.returncode == 0, r2.stdout + r2.stderr
     _, disp2, _, stress2 = stdb.results(stdb.decode(out.read_bytes()))
     assert np.array_equal(disp2, disp) and np.array_equal(stress2, stress)
+
+
+def test_stan_solver_cli_cholesky(oracle, tmp_path):
+    """Analysis.LinSolver = "Cholesky" takes the direct path (Solver.cs:163) and prints its console lines."""
+    from stan_b200 import build
+    host = build.build_host()
+    m = mesh.beam(4, 4, 12, jitter=True)
+    m.lin_solver = "Cholesky"
+    src, out = tmp_path / "model.STdb", tmp_path / "solved.STdb"
+    src.write_bytes(stdb.encode(stdb.from_model(m)))
+    r = subprocess.run([host, str(src), "-o", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for line in ("Linear system K*U=F:", "- Cholesky decomposition:   Done", "NORMAL termination (type 1)",
+                 "Total time to solve K*U=F:", "Stress recovery:"):
+        assert line in r.stdout, line                            # SolverFunctions.cs:384-441
+    db = stdb.decode(out.read_bytes())
+    assert db.analysis.linsolver == "Cholesky"
+    ni, disp, strain, stress = stdb.results(db)
+    red, _ = oracle.spc_reduction(m, ni)
+    K = oracle.assemble_upper(m, ni, red)
+    xo, tt, _ = oracle.cholesky_skyline(K, oracle.build_rhs(m, ni, red))
+    ou = oracle.include_bc_dof(red, xo).reshape(-1, 3)[ni]
+    assert tt == 1 and np.abs(disp - ou).max() <= 1e-10 * np.abs(ou).max()
+    # a solver name the path does not provide is refused, not silently replaced
+    m.lin_solver = "LU"
+    src.write_bytes(stdb.encode(stdb.from_model(m)))
+    r = subprocess.run([host, str(src), "-o", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 3 and "LU" in r.stderr

@@ -204,6 +204,37 @@ def test_lincg_termination_codes(oracle):
     assert rep.terminationtype != 1
 
 
+def test_cholesky_skyline_against_dense_and_theory(oracle):
+    """LinearSolver_Cholesky restatement (SolverFunctions.cs:332-444): pinned by numpy's dense Cholesky,
+    the envelope definition, beam theory, and the -3 / zeros contract for a matrix that is not SPD."""
+    m = mesh.beam(4, 4, 50)
+    ni = oracle.assign_dof(m); red, _ = oracle.spc_reduction(m, ni)
+    F = oracle.build_rhs(m, ni, red)
+    K = oracle.assemble_upper(m, ni, red)
+    x, tt, env = oracle.cholesky_skyline(K, F)
+    A = K.to_scipy_full().toarray()
+    L = np.linalg.cholesky(A)
+    xd = np.linalg.solve(L.T, np.linalg.solve(L, F))
+    assert tt == 1 and np.linalg.norm(x - xd) / np.linalg.norm(xd) < 1e-11
+    rp, col, _ = K.arrays()
+    first = np.arange(K.n)
+    for i in range(K.n):
+        c = col[rp[i]:rp[i + 1]]
+        first[c] = np.minimum(first[c], i)
+    assert env == int((np.arange(K.n) - first + 1).sum())         # sparseconverttosks envelope
+    U = oracle.include_bc_dof(red, x)
+    tip = U[3 * ni[m.load_node]].mean()
+    EI, Lb, G, Ar = 210000.0 * 4**4 / 12, 50.0, 80769.23, 16.0
+    theory = 1000 * Lb**3 / (3 * EI) + 1000 * Lb / (5.0 / 6.0 * G * Ar)
+    assert abs(tip - theory) / theory < 0.06
+    xc, rep = oracle.lincg(K, F, oracle.cg_opts(epsf=1e-10, maxits=5000, merit_check=0))
+    assert rep.terminationtype == 1 and np.linalg.norm(x - xc) / np.linalg.norm(x) < 1e-8
+    m.mat_E = -m.mat_E                                            # negative definite: no factor
+    Kn = oracle.assemble_upper(m, ni, red)
+    xn, tt, _ = oracle.cholesky_skyline(Kn, F)
+    assert tt == -3 and not xn.any()                              # "filled by zeros" (SolverFunctions.cs:420)
+
+
 def test_recovery_patch_test(oracle):
     m = mesh.beam(3, 3, 3, jitter=True)
     ni = oracle.assign_dof(m)
