@@ -13,6 +13,7 @@
 // block is padded with identity rows.  Every sum has a fixed order, so results are reproducible.
 // Single GPU: a skyline that does not fit one device is beyond what a direct solver is for here.
 #include "common.cuh"
+#include "bulk.cuh"
 
 namespace stan {
 
@@ -73,39 +74,59 @@ __global__ void k_band_pad(int64_t n, int64_t npad, BandDev B) {
     B.blk(J, J)[rr * CB + rr] = 1.0;
 }
 
+// Programmatic dependent launch: every step kernel lets its successor start early and run its
+// prologue (loads that do not depend on the predecessor) while the predecessor drains; pdl_wait()
+// returns once the predecessor grid has completed and its stores are visible.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- panel: diagonal block Cholesky + row of triangular solves -------------------------------
-// 256 threads.  Every CTA factorises the 64x64 diagonal block in shared memory (identical arithmetic,
-// so identical bits; it is cheaper than a second launch per block row), CTA 0 stores it, and each
-// 64-thread quarter then solves U_KK^T X = A_KJ for one block J with a column of X per thread held
-// in registers (no barriers in the 2016-FMA substitution; U_KK reads are shared-memory broadcasts).
+// 256 threads.  Every CTA factorises the 64x64 diagonal block (identical arithmetic, so identical
+// bits; cheaper than a second launch per block row) and CTA 0 stores it.  The block lives in
+// registers: thread (c, q) owns A[q + 4i][c], i < 16.  Step j costs one barrier: the owners publish
+// the raw row j, then every thread scales it by rsqrt(a_jj) itself and applies the rank-1 update to
+// its 16 entries.  The stored diagonal is sqrt(a_jj) exactly; off-diagonals are a_jc * rsqrt(a_jj)
+// (within 1 ulp of a_jc / sqrt(a_jj), the reference's form).  Each 64-thread quarter then solves
+// U_KK^T X = A_KJ for one block J, a column of X per thread in registers: no barriers in the
+// 2016-FMA substitution, U_KK reads are shared-memory broadcasts, diagonals enter as reciprocals.
 constexpr int PANEL_TILES = 4;
 __global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, int *__restrict__ err) {
     __shared__ double D[CBB];
-    __shared__ double dg[CB];
+    __shared__ double rowbuf[2][CB];
+    __shared__ double rinv[CB];
     const int tid = threadIdx.x;
-    double *gkk = B.blk(K, K);
-    for (int i = tid; i < CBB; i += 256) D[i] = gkk[i];
-    __syncthreads();
     const int c = tid & 63, rq = tid >> 6;
+    pdl_trigger();
+    pdl_wait();
+    double *gkk = B.blk(K, K);
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = gkk[(rq + 4 * i) * CB + c];
+    bool bad = false;
+#pragma unroll
     for (int j = 0; j < CB; j++) {
-        double djj = D[j * CB + j];
-        if (!(djj > 0.0)) {                         // sparsecholeskyskyline returns false here
-            if (tid == 0 && blockIdx.x == 0) atomicOr(err + ERR_NOT_SPD, 1);
-            djj = 1.0;
+        const int ij = j >> 2, qj = j & 3;
+        double *rb = rowbuf[j & 1];
+        if (rq == qj) rb[c] = a[ij];
+        __syncthreads();
+        double ajj = rb[j];
+        if (!(ajj > 0.0)) { bad = true; ajj = 1.0; }      // sparsecholeskyskyline returns false here
+        const double rs = rsqrt(ajj);
+        const double ujc = rb[c] * rs;
+        if (rq == qj && c >= j) D[j * CB + c] = (c == j) ? sqrt(ajj) : ujc;
+#pragma unroll
+        for (int i = ij; i < 16; i++) {
+            const int r = rq + 4 * i;
+            if (r > j && r <= c) a[i] -= (rb[r] * rs) * ujc;
         }
-        const double sj = sqrt(djj);
-        if (tid < CB && tid > j) D[j * CB + tid] = D[j * CB + tid] / sj;
-        if (tid == j) dg[j] = sj;
-        __syncthreads();
-        const double ujc = D[j * CB + c];
-        for (int r = j + 1 + rq; r <= c; r += 4) D[r * CB + c] -= D[j * CB + r] * ujc;
-        __syncthreads();
     }
-    if (tid < CB) D[tid * CB + tid] = dg[tid];
     __syncthreads();
+    if (tid < CB) rinv[tid] = 1.0 / D[tid * CB + tid];
+    if (bad && tid == 0 && blockIdx.x == 0) atomicOr(err + ERR_NOT_SPD, 1);
     if (blockIdx.x == 0)
         for (int i = tid; i < CBB; i += 256)
             if ((i >> 6) <= (i & 63)) gkk[i] = D[i];
+    __syncthreads();
 
     const int jt = blockIdx.x * PANEL_TILES + rq;
     if (jt >= m) return;
@@ -115,7 +136,7 @@ __global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, 
     for (int r = 0; r < CB; r++) t[r] = g[r * CB + c];
 #pragma unroll
     for (int r = 0; r < CB; r++) {
-        t[r] = t[r] / D[r * CB + r];
+        t[r] = t[r] * rinv[r];
 #pragma unroll
         for (int r2 = r + 1; r2 < CB; r2++) t[r2] -= D[r * CB + r2] * t[r];
     }
@@ -124,85 +145,132 @@ __global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, 
 }
 
 // ---- trailing update: C_IJ -= U_KI^T U_KJ ----------------------------------------------------
-// One 64x64 block per CTA, 128 threads, 8x4 accumulators per thread: per k a thread reads 8 values
-// of U_KI (two addresses per warp: broadcast) and 2+2 of U_KJ (conflict-free 16-byte lanes), 32 FMAs.
-__global__ void __launch_bounds__(128) k_chol_update(BandDev B, int K) {
-    const int a = blockIdx.x, b = blockIdx.y;
-    if (a > b) return;
-    extern __shared__ __align__(16) double sm[];
-    double *As = sm, *Bs = sm + CBB;
+// A CTA owns up to `ch` consecutive blocks of one block row I: U_KI is fetched once, the U_KJ
+// blocks stream through a two-deep shared-memory ring with cp.async.bulk (one elected thread, byte-
+// counting mbarriers), and the C block is prefetched into registers before the 64-deep product so
+// its latency hides behind the FMAs.  128 threads, 8x4 accumulators each: per k a thread reads 8
+// values of U_KI (two addresses per warp: broadcast) and 2+2 of U_KJ (conflict-free 16-byte lanes)
+// for 32 FMAs, so the loop is bound by the FP64 pipe.  Grid (chunks, rows); blockIdx.x runs fastest,
+// which dispatches block row K+1 — the next panel's input — first.
+constexpr uint32_t BLK_BYTES = CBB * sizeof(double);
+__global__ void __launch_bounds__(128) k_chol_update(BandDev B, int K, int m, int ch) {
+    const int a = blockIdx.y;
+    const int b0 = a + blockIdx.x * ch;
+    if (b0 >= m) return;
+    const int nb = min(ch, m - b0);
+    extern __shared__ __align__(128) double sm[];
+    __shared__ uint64_t bar[3];
+    double *As = sm;
     const int tid = threadIdx.x;
-    const int I = K + 1 + a, J = K + 1 + b;
-    {
-        const double2 *ga = reinterpret_cast<const double2 *>(B.blk(K, I));
-        const double2 *gb = reinterpret_cast<const double2 *>(B.blk(K, J));
-        double2 *sa = reinterpret_cast<double2 *>(As), *sb = reinterpret_cast<double2 *>(Bs);
-#pragma unroll 8
-        for (int i = tid; i < CBB / 2; i += 128) { sa[i] = ga[i]; sb[i] = gb[i]; }
+    const int I = K + 1 + a;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_trigger();
     __syncthreads();
+    pdl_wait();
+    if (tid == 0) {
+        mbar_expect_tx(&bar[2], BLK_BYTES); bulk_g2s(As, B.blk(K, I), BLK_BYTES, &bar[2]);
+        mbar_expect_tx(&bar[0], BLK_BYTES); bulk_g2s(sm + CBB, B.blk(K, K + 1 + b0), BLK_BYTES, &bar[0]);
+        if (nb > 1) { mbar_expect_tx(&bar[1], BLK_BYTES); bulk_g2s(sm + 2 * CBB, B.blk(K, K + 2 + b0), BLK_BYTES, &bar[1]); }
+    }
     const int ty = tid >> 4, tx = tid & 15;
-    double acc[8][4];
+    for (int t = 0; t < nb; t++) {
+        const int J = K + 1 + b0 + t;
+        double *gc = B.blk(I, J);
+        double2 c0[8], c1[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < CB; k++) {
-        double av[8], bv[4];
-        const double2 *pa = reinterpret_cast<const double2 *>(As + k * CB + ty * 8);
-#pragma unroll
-        for (int i = 0; i < 4; i++) { double2 v = pa[i]; av[2 * i] = v.x; av[2 * i + 1] = v.y; }
-        const double2 b0 = *reinterpret_cast<const double2 *>(Bs + k * CB + 2 * tx);
-        const double2 b1 = *reinterpret_cast<const double2 *>(Bs + k * CB + 32 + 2 * tx);
-        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b1.x; bv[3] = b1.y;
+        for (int i = 0; i < 8; i++) {
+            c0[i] = *reinterpret_cast<const double2 *>(gc + (ty * 8 + i) * CB + 2 * tx);
+            c1[i] = *reinterpret_cast<const double2 *>(gc + (ty * 8 + i) * CB + 32 + 2 * tx);
+        }
+        if (t == 0) mbar_wait(&bar[2], 0);
+        mbar_wait(&bar[t & 1], (uint32_t)((t >> 1) & 1));
+        const double *Bs = sm + (1 + (t & 1)) * CBB;
+        double acc[8][4];
 #pragma unroll
         for (int i = 0; i < 8; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] += av[i] * bv[j];
-    }
-    double *gc = B.blk(I, J);
+            for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < CB; k++) {
+            double av[8], bv[4];
+            const double2 *pa = reinterpret_cast<const double2 *>(As + k * CB + ty * 8);
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        double2 *p0 = reinterpret_cast<double2 *>(gc + (ty * 8 + i) * CB + 2 * tx);
-        double2 *p1 = reinterpret_cast<double2 *>(gc + (ty * 8 + i) * CB + 32 + 2 * tx);
-        double2 c0 = *p0, c1 = *p1;
-        c0.x -= acc[i][0]; c0.y -= acc[i][1]; c1.x -= acc[i][2]; c1.y -= acc[i][3];
-        *p0 = c0; *p1 = c1;
+            for (int i = 0; i < 4; i++) { double2 v = pa[i]; av[2 * i] = v.x; av[2 * i + 1] = v.y; }
+            const double2 b0v = *reinterpret_cast<const double2 *>(Bs + k * CB + 2 * tx);
+            const double2 b1v = *reinterpret_cast<const double2 *>(Bs + k * CB + 32 + 2 * tx);
+            bv[0] = b0v.x; bv[1] = b0v.y; bv[2] = b1v.x; bv[3] = b1v.y;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] += av[i] * bv[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            c0[i].x -= acc[i][0]; c0[i].y -= acc[i][1]; c1[i].x -= acc[i][2]; c1[i].y -= acc[i][3];
+            *reinterpret_cast<double2 *>(gc + (ty * 8 + i) * CB + 2 * tx) = c0[i];
+            *reinterpret_cast<double2 *>(gc + (ty * 8 + i) * CB + 32 + 2 * tx) = c1[i];
+        }
+        __syncthreads();                                      // ring slot t&1 is free again
+        if (tid == 0 && t + 2 < nb) {
+            mbar_expect_tx(&bar[t & 1], BLK_BYTES);
+            bulk_g2s(sm + (1 + (t & 1)) * CBB, B.blk(K, J + 2), BLK_BYTES, &bar[t & 1]);
+        }
     }
 }
 
 // ---- U^T y = b, block row K: y_K = U_KK^-T w_K, then w_J -= U_KJ^T y_K for J in (K, E[K]] -------
+// The factor is final, so the diagonal block and this CTA's off-diagonal block are fetched before
+// pdl_wait(); only w_K depends on the previous step.  Substitution by one warp (2 entries per lane),
+// diagonals as reciprocals computed up front, so the 64-step chain is shuffle + multiply + FMA.
 __global__ void __launch_bounds__(256) k_chol_fwd(BandDev B, int K, int m, double *__restrict__ w,
                                                   double *__restrict__ y) {
     __shared__ double D[CBB];
     __shared__ double ys[CB];
     __shared__ double part[4][CB];
     const int tid = threadIdx.x, lane = tid & 31;
+    const int c = tid & 63, q = tid >> 6;
+    pdl_trigger();
     const double *gkk = B.blk(K, K);
-    for (int i = tid; i < CBB; i += 256) D[i] = gkk[i];
+#pragma unroll
+    for (int i = 0; i < CBB / 256; i++) D[tid + 256 * i] = gkk[tid + 256 * i];
+    const bool has = (int)blockIdx.x < m;
+    const int J = K + 1 + blockIdx.x;
+    double gt[16];
+    if (has) {
+        const double *g = B.blk(K, J);
+#pragma unroll
+        for (int i = 0; i < 16; i++) gt[i] = g[(q * 16 + i) * CB + c];
+    }
+    pdl_wait();
     if (tid < CB) ys[tid] = w[(int64_t)K * CB + tid];
     __syncthreads();
     if (tid < 32) {
         double v0 = ys[lane], v1 = ys[lane + 32];
-        for (int r = 0; r < CB; r++) {
-            double yr = (r < 32) ? __shfl_sync(0xffffffffu, v0, r) : __shfl_sync(0xffffffffu, v1, r - 32);
-            yr = yr / D[r * CB + r];
-            if (lane == (r & 31)) { if (r < 32) v0 = yr; else v1 = yr; }
+        const double ri0 = 1.0 / D[lane * CB + lane], ri1 = 1.0 / D[(lane + 32) * CB + lane + 32];
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+            const double yr = __shfl_sync(0xffffffffu, v0 * ri0, r);
+            if (lane == r) v0 = yr;
             if (lane > r) v0 -= D[r * CB + lane] * yr;
+            v1 -= D[r * CB + lane + 32] * yr;
+        }
+#pragma unroll 8
+        for (int r = 32; r < CB; r++) {
+            const double yr = __shfl_sync(0xffffffffu, v1 * ri1, r - 32);
+            if (lane + 32 == r) v1 = yr;
             if (lane + 32 > r) v1 -= D[r * CB + lane + 32] * yr;
         }
         ys[lane] = v0; ys[lane + 32] = v1;
     }
     __syncthreads();
     if (blockIdx.x == 0 && tid < CB) y[(int64_t)K * CB + tid] = ys[tid];
-    if ((int)blockIdx.x >= m) return;
-    const int J = K + 1 + blockIdx.x;
-    const double *g = B.blk(K, J);
-    const int c = tid & 63, q = tid >> 6;
+    if (!has) return;
     double p = 0.0;
-#pragma unroll 4
-    for (int r = q * 16; r < q * 16 + 16; r++) p += g[r * CB + c] * ys[r];
+#pragma unroll
+    for (int i = 0; i < 16; i++) p += gt[i] * ys[q * 16 + i];
     part[q][c] = p;
     __syncthreads();
     if (q == 0) w[(int64_t)J * CB + c] -= ((part[0][c] + part[1][c]) + part[2][c]) + part[3][c];
@@ -214,32 +282,71 @@ __global__ void __launch_bounds__(256) k_chol_bwd(BandDev B, int J, int cnt, dou
     __shared__ double D[CB * (CB + 1)];
     __shared__ double xs[CB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
     const double *gjj = B.blk(J, J);
-    for (int i = tid; i < CBB; i += 256) D[(i >> 6) * (CB + 1) + (i & 63)] = gjj[i];
+#pragma unroll
+    for (int i = 0; i < CBB / 256; i++) {
+        const int e = tid + 256 * i;
+        D[(e >> 6) * (CB + 1) + (e & 63)] = gjj[e];
+    }
+    const bool has = (int)blockIdx.x < cnt;
+    const int I = B.F[J] + blockIdx.x;
+    double g0[8], g1[8];
+    if (has) {
+        const double *g = B.blk(I, J);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { g0[i] = g[(warp * 8 + i) * CB + lane]; g1[i] = g[(warp * 8 + i) * CB + lane + 32]; }
+    }
+    pdl_wait();
     if (tid < CB) xs[tid] = y[(int64_t)J * CB + tid];
     __syncthreads();
     if (tid < 32) {
         double v0 = xs[lane], v1 = xs[lane + 32];
-        for (int c = CB - 1; c >= 0; c--) {
-            double xc = (c < 32) ? __shfl_sync(0xffffffffu, v0, c) : __shfl_sync(0xffffffffu, v1, c - 32);
-            xc = xc / D[c * (CB + 1) + c];
-            if (lane == (c & 31)) { if (c < 32) v0 = xc; else v1 = xc; }
-            if (lane < c) v0 -= D[lane * (CB + 1) + c] * xc;
-            if (lane + 32 < c) v1 -= D[(lane + 32) * (CB + 1) + c] * xc;
+        const double ri0 = 1.0 / D[lane * (CB + 1) + lane], ri1 = 1.0 / D[(lane + 32) * (CB + 1) + lane + 32];
+#pragma unroll 8
+        for (int cc = CB - 1; cc >= 32; cc--) {
+            const double xc = __shfl_sync(0xffffffffu, v1 * ri1, cc - 32);
+            if (lane + 32 == cc) v1 = xc;
+            if (lane + 32 < cc) v1 -= D[(lane + 32) * (CB + 1) + cc] * xc;
+            v0 -= D[lane * (CB + 1) + cc] * xc;
+        }
+#pragma unroll 8
+        for (int cc = 31; cc >= 0; cc--) {
+            const double xc = __shfl_sync(0xffffffffu, v0 * ri0, cc);
+            if (lane == cc) v0 = xc;
+            if (lane < cc) v0 -= D[lane * (CB + 1) + cc] * xc;
         }
         xs[lane] = v0; xs[lane + 32] = v1;
     }
     __syncthreads();
     if (blockIdx.x == 0 && tid < CB) x[(int64_t)J * CB + tid] = xs[tid];
-    if ((int)blockIdx.x >= cnt) return;
-    const int I = B.F[J] + blockIdx.x;
-    const double *g = B.blk(I, J);
-    for (int r = warp * 8; r < warp * 8 + 8; r++) {
-        double p = g[r * CB + lane] * xs[lane] + g[r * CB + lane + 32] * xs[lane + 32];
+    if (!has) return;
+    const double x0 = xs[lane], x1 = xs[lane + 32];
+    double p[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        if (lane == 0) y[(int64_t)I * CB + r] -= p;
+    for (int i = 0; i < 8; i++) p[i] = g0[i] * x0 + g1[i] * x1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < 8; i++) p[i] += __shfl_xor_sync(0xffffffffu, p[i], o);
+    if (lane < 8) {
+        double v = p[0];
+#pragma unroll
+        for (int i = 1; i < 8; i++) if (lane == i) v = p[i];
+        y[(int64_t)I * CB + warp * 8 + lane] -= v;
     }
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_step(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 }  // namespace
@@ -315,19 +422,24 @@ int solve_cholesky(stan_handle *h, stan_chol_report *rep) {
     // ---- factorisation ----
     static bool attr_set = false;
     if (!attr_set) {
-        STAN_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CBB * (int)sizeof(double)));
+        STAN_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * CBB * (int)sizeof(double)));
         attr_set = true;
     }
     STAN_CUDA(cudaEventRecord(h->ev1, s));
     double flops = 0.0;
     const double b3 = (double)CB * CB * CB;
+    static const bool use_pdl = !(getenv("STAN_PDL") && atoi(getenv("STAN_PDL")) == 0);
     for (int64_t K = 0; K < nbk; K++) {
         const int m = E[K] - (int)K;
-        k_chol_panel<<<std::max(1, div_up(m, PANEL_TILES)), 256, 0, s>>>(B, (int)K, m, h->d_err.p);
+        STAN_CUDA(launch_step(k_chol_panel, dim3(std::max(1, div_up(m, PANEL_TILES))), dim3(256), 0, s, use_pdl && K > 0,
+                              B, (int)K, m, h->d_err.p));
         launches++;
         flops += b3 / 3 + (double)m * b3;
         if (m > 0) {
-            k_chol_update<<<dim3(m, m), 128, 2 * CBB * sizeof(double), s>>>(B, (int)K);
+            // blocks per CTA along a row: long strips reuse U_KI, but small trailing matrices need the CTAs
+            const int ch = std::max(1, std::min(4, (m * (m + 1) / 2) / (4 * h->sm_count)));
+            STAN_CUDA(launch_step(k_chol_update, dim3(div_up(m, ch), m), dim3(128), 3 * CBB * sizeof(double), s, use_pdl,
+                                  B, (int)K, m, ch));
             launches++;
             flops += (double)m * (m + 1) * b3;      // m(m+1)/2 blocks x 2*64^3
         }
@@ -335,13 +447,15 @@ int solve_cholesky(stan_handle *h, stan_chol_report *rep) {
     STAN_CUDA(cudaEventRecord(h->ev2, s));
 
     // ---- triangular solves ----
+    // the first sweep kernel must see the finished factor before its prologue: no early start for it
     for (int64_t K = 0; K < nbk; K++) {
         const int m = E[K] - (int)K;
-        k_chol_fwd<<<std::max(1, m), 256, 0, s>>>(B, (int)K, m, w.p, y.p);
+        STAN_CUDA(launch_step(k_chol_fwd, dim3(std::max(1, m)), dim3(256), 0, s, use_pdl && K > 0, B, (int)K, m, w.p, y.p));
     }
     for (int64_t J = nbk - 1; J >= 0; J--) {
         const int cnt = (int)J - F[J];
-        k_chol_bwd<<<std::max(1, cnt), 256, 0, s>>>(B, (int)J, cnt, y.p, x.p);
+        STAN_CUDA(launch_step(k_chol_bwd, dim3(std::max(1, cnt)), dim3(256), 0, s, use_pdl && J < nbk - 1, B, (int)J, cnt,
+                              y.p, x.p));
     }
     launches += 2 * nbk;
     STAN_CUDA(cudaEventRecord(h->ev3, s));
