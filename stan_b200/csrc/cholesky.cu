@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, 
         if (!(ajj > 0.0)) { bad = true; ajj = 1.0; }      // sparsecholeskyskyline returns false here
         const double rs = rsqrt(ajj);
         const double ujc = rb[c] * rs;
-        if (rq == qj && c >= j) D[j * CB + c] = (c == j) ? sqrt(ajj) : ujc;
+        if (rq == qj && c >= j) D[j * CB + c] = (c == j) ? ajj : ujc;     // diagonal: raw pivot, rooted below
 #pragma unroll
         for (int i = ij; i < 16; i++) {
             const int r = rq + 4 * i;
@@ -121,7 +121,12 @@ __global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, 
         }
     }
     __syncthreads();
-    if (tid < CB) rinv[tid] = 1.0 / D[tid * CB + tid];
+    if (tid < CB) {                                       // exact square roots, off the elimination chain
+        const double d = sqrt(D[tid * CB + tid]);
+        D[tid * CB + tid] = d;
+        rinv[tid] = 1.0 / d;
+    }
+    __syncthreads();
     if (bad && tid == 0 && blockIdx.x == 0) atomicOr(err + ERR_NOT_SPD, 1);
     if (blockIdx.x == 0)
         for (int i = tid; i < CBB; i += 256)
@@ -145,31 +150,62 @@ __global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, 
 }
 
 // ---- trailing update: C_IJ -= U_KI^T U_KJ ----------------------------------------------------
-// A CTA owns up to `ch` consecutive blocks of one block row I: U_KI is fetched once, the U_KJ
+// 128 threads per 64x64 block, 8x4 accumulators each: per k a thread reads 8 values of U_KI (two
+// addresses per warp: broadcast) and 2+2 of U_KJ (conflict-free 16-byte lanes) for 32 FMAs, so the
+// loop is bound by the FP64 pipe.
+constexpr uint32_t BLK_BYTES = CBB * sizeof(double);
+
+__device__ __forceinline__ void gemm64(const double *__restrict__ As, const double *__restrict__ Bs, int ty, int tx,
+                                       double (&acc)[8][4]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < CB; k++) {
+        double av[8], bv[4];
+        const double2 *pa = reinterpret_cast<const double2 *>(As + k * CB + ty * 8);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { double2 v = pa[i]; av[2 * i] = v.x; av[2 * i + 1] = v.y; }
+        const double2 b0v = *reinterpret_cast<const double2 *>(Bs + k * CB + 2 * tx);
+        const double2 b1v = *reinterpret_cast<const double2 *>(Bs + k * CB + 32 + 2 * tx);
+        bv[0] = b0v.x; bv[1] = b0v.y; bv[2] = b1v.x; bv[3] = b1v.y;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] += av[i] * bv[j];
+    }
+}
+// a thread's 8x4 piece of a row-major 64x64 block: rows ty*8.., columns {2tx, 2tx+1, 32+2tx, 33+2tx}
+__device__ __forceinline__ void load_piece(const double *blk, int ty, int tx, double2 (&c0)[8], double2 (&c1)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        c0[i] = *reinterpret_cast<const double2 *>(blk + (ty * 8 + i) * CB + 2 * tx);
+        c1[i] = *reinterpret_cast<const double2 *>(blk + (ty * 8 + i) * CB + 32 + 2 * tx);
+    }
+}
+__device__ __forceinline__ void sub_store_piece(double *blk, int ty, int tx, double2 (&c0)[8], double2 (&c1)[8],
+                                                const double (&acc)[8][4], bool sub) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (sub) { c0[i].x -= acc[i][0]; c0[i].y -= acc[i][1]; c1[i].x -= acc[i][2]; c1[i].y -= acc[i][3]; }
+        *reinterpret_cast<double2 *>(blk + (ty * 8 + i) * CB + 2 * tx) = c0[i];
+        *reinterpret_cast<double2 *>(blk + (ty * 8 + i) * CB + 32 + 2 * tx) = c1[i];
+    }
+}
+
+// One CTA owns up to `ch` consecutive blocks of block row I = K+1+a: U_KI is fetched once, the U_KJ
 // blocks stream through a two-deep shared-memory ring with cp.async.bulk (one elected thread, byte-
 // counting mbarriers), and the C block is prefetched into registers before the 64-deep product so
-// its latency hides behind the FMAs.  128 threads, 8x4 accumulators each: per k a thread reads 8
-// values of U_KI (two addresses per warp: broadcast) and 2+2 of U_KJ (conflict-free 16-byte lanes)
-// for 32 FMAs, so the loop is bound by the FP64 pipe.  Grid (chunks, rows); blockIdx.x runs fastest,
-// which dispatches block row K+1 — the next panel's input — first.
-constexpr uint32_t BLK_BYTES = CBB * sizeof(double);
-__global__ void __launch_bounds__(128) k_chol_update(BandDev B, int K, int m, int ch) {
-    const int a = blockIdx.y;
-    const int b0 = a + blockIdx.x * ch;
+// its latency hides behind the FMAs.  Call after pdl_wait() with the three mbarriers initialised.
+__device__ __forceinline__ void update_strip(const BandDev &B, int K, int m, int ch, int a, int chunk, double *sm,
+                                             uint64_t *bar) {
+    const int b0 = a + chunk * ch;
     if (b0 >= m) return;
     const int nb = min(ch, m - b0);
-    extern __shared__ __align__(128) double sm[];
-    __shared__ uint64_t bar[3];
     double *As = sm;
     const int tid = threadIdx.x;
     const int I = K + 1 + a;
-    if (tid == 0) {
-        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    pdl_trigger();
-    __syncthreads();
-    pdl_wait();
     if (tid == 0) {
         mbar_expect_tx(&bar[2], BLK_BYTES); bulk_g2s(As, B.blk(K, I), BLK_BYTES, &bar[2]);
         mbar_expect_tx(&bar[0], BLK_BYTES); bulk_g2s(sm + CBB, B.blk(K, K + 1 + b0), BLK_BYTES, &bar[0]);
@@ -180,45 +216,34 @@ __global__ void __launch_bounds__(128) k_chol_update(BandDev B, int K, int m, in
         const int J = K + 1 + b0 + t;
         double *gc = B.blk(I, J);
         double2 c0[8], c1[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            c0[i] = *reinterpret_cast<const double2 *>(gc + (ty * 8 + i) * CB + 2 * tx);
-            c1[i] = *reinterpret_cast<const double2 *>(gc + (ty * 8 + i) * CB + 32 + 2 * tx);
-        }
+        load_piece(gc, ty, tx, c0, c1);
         if (t == 0) mbar_wait(&bar[2], 0);
         mbar_wait(&bar[t & 1], (uint32_t)((t >> 1) & 1));
-        const double *Bs = sm + (1 + (t & 1)) * CBB;
         double acc[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-#pragma unroll 4
-        for (int k = 0; k < CB; k++) {
-            double av[8], bv[4];
-            const double2 *pa = reinterpret_cast<const double2 *>(As + k * CB + ty * 8);
-#pragma unroll
-            for (int i = 0; i < 4; i++) { double2 v = pa[i]; av[2 * i] = v.x; av[2 * i + 1] = v.y; }
-            const double2 b0v = *reinterpret_cast<const double2 *>(Bs + k * CB + 2 * tx);
-            const double2 b1v = *reinterpret_cast<const double2 *>(Bs + k * CB + 32 + 2 * tx);
-            bv[0] = b0v.x; bv[1] = b0v.y; bv[2] = b1v.x; bv[3] = b1v.y;
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[i][j] += av[i] * bv[j];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            c0[i].x -= acc[i][0]; c0[i].y -= acc[i][1]; c1[i].x -= acc[i][2]; c1[i].y -= acc[i][3];
-            *reinterpret_cast<double2 *>(gc + (ty * 8 + i) * CB + 2 * tx) = c0[i];
-            *reinterpret_cast<double2 *>(gc + (ty * 8 + i) * CB + 32 + 2 * tx) = c1[i];
-        }
+        gemm64(As, sm + (1 + (t & 1)) * CBB, ty, tx, acc);
+        sub_store_piece(gc, ty, tx, c0, c1, acc, true);
         __syncthreads();                                      // ring slot t&1 is free again
         if (tid == 0 && t + 2 < nb) {
             mbar_expect_tx(&bar[t & 1], BLK_BYTES);
             bulk_g2s(sm + (1 + (t & 1)) * CBB, B.blk(K, J + 2), BLK_BYTES, &bar[t & 1]);
         }
     }
+}
+
+// Grid (chunks, rows); blockIdx.x runs fastest, which dispatches block row K+1 — the next panel's
+// input — first.
+__global__ void __launch_bounds__(128) k_chol_update(BandDev B, int K, int m, int ch) {
+    extern __shared__ __align__(128) double sm[];
+    __shared__ uint64_t bar[3];
+    if ((int)blockIdx.y + (int)blockIdx.x * ch >= m) return;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    pdl_trigger();
+    __syncthreads();
+    pdl_wait();
+    update_strip(B, K, m, ch, blockIdx.y, blockIdx.x, sm, bar);
 }
 
 // ---- U^T y = b, block row K: y_K = U_KK^-T w_K, then w_J -= U_KJ^T y_K for J in (K, E[K]] -------
