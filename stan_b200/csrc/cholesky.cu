@@ -89,8 +89,9 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // (within 1 ulp of a_jc / sqrt(a_jj), the reference's form).  Each 64-thread quarter then solves
 // U_KK^T X = A_KJ for one block J, a column of X per thread in registers: no barriers in the
 // 2016-FMA substitution, U_KK reads are shared-memory broadcasts, diagonals enter as reciprocals.
-constexpr int PANEL_TILES = 4;
-__global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, int *__restrict__ err) {
+// `tiles` (1, 2 or 4) quarters of a CTA take a block each: one per CTA while the row is short, so the
+// substitutions spread over the SMs instead of sharing one FP64 pipe.
+__global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, int tiles, int *__restrict__ err) {
     __shared__ double D[CBB];
     __shared__ double rowbuf[2][CB];
     __shared__ double rinv[CB];
@@ -133,8 +134,8 @@ __global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, 
             if ((i >> 6) <= (i & 63)) gkk[i] = D[i];
     __syncthreads();
 
-    const int jt = blockIdx.x * PANEL_TILES + rq;
-    if (jt >= m) return;
+    const int jt = blockIdx.x * tiles + rq;
+    if (rq >= tiles || jt >= m) return;
     double *g = B.blk(K, K + 1 + jt);
     double t[CB];
 #pragma unroll
@@ -456,8 +457,9 @@ int solve_cholesky(stan_handle *h, stan_chol_report *rep) {
     static const bool use_pdl = !(getenv("STAN_PDL") && atoi(getenv("STAN_PDL")) == 0);
     for (int64_t K = 0; K < nbk; K++) {
         const int m = E[K] - (int)K;
-        STAN_CUDA(launch_step(k_chol_panel, dim3(std::max(1, div_up(m, PANEL_TILES))), dim3(256), 0, s, use_pdl && K > 0,
-                              B, (int)K, m, h->d_err.p));
+        const int tiles = m > 2 * h->sm_count ? 4 : m > h->sm_count ? 2 : 1;
+        STAN_CUDA(launch_step(k_chol_panel, dim3(std::max(1, div_up(m, tiles))), dim3(256), 0, s, use_pdl && K > 0,
+                              B, (int)K, m, tiles, h->d_err.p));
         launches++;
         flops += b3 / 3 + (double)m * b3;
         if (m > 0) {
