@@ -158,7 +158,9 @@ int stan_get_element_range(stan_handle *h, int64_t *first, int64_t *last);
 /* --- post-processing: Part.Load_Scalar, Part.cs:231-528 ------------------ */
 /* 24 scalar fields (displacement x/y/z/total, stress xx..xz, P1..P3, von Mises, strain xx..xz,
  * P1..P3, effective strain) as float32: cell = n_elem x 24 x {max, average, min} over the element's
- * nodes, point = n_nodes x 24 averaged over the elements containing the node (NodeLib order). */
+ * nodes, point = n_nodes x 24 averaged over the elements containing the node (NodeLib order).
+ * Multi-GPU: cell covers this rank's element slice (stan_get_element_range), point covers its rows
+ * (stan_get_partition) in DOF-map order: point[r - first_row] belongs to the node with DOF[0]/3 == r. */
 int stan_postprocess(stan_handle *h, double *device_ms);
 int stan_get_scalars(stan_handle *h, float *cell, float *point);
 

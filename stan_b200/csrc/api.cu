@@ -367,8 +367,9 @@ int stan_postprocess(stan_handle *h, double *ms) {
 int stan_get_scalars(stan_handle *h, float *cell, float *point) {
     STAN_TRY(check(h));
     if (!h->postprocessed || !h->recovered) { set_error("stan_get_scalars before stan_postprocess"); return STAN_E_STATE; }
-    if (cell) STAN_CUDA(cudaMemcpyAsync(cell, h->d_cell.p, (size_t)h->n_elem * 72 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    if (point) STAN_CUDA(cudaMemcpyAsync(point, h->d_point.p, (size_t)h->n_nodes * 24 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    // one GPU: every element / every node; partitioned: the rank's element slice and its rows
+    if (cell) STAN_CUDA(cudaMemcpyAsync(cell, h->d_cell.p, (size_t)(h->elem1 - h->elem0) * 72 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (point) STAN_CUDA(cudaMemcpyAsync(point, h->d_point.p, (size_t)(h->row1 - h->row0) * 24 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     STAN_CUDA(cudaStreamSynchronize(h->stream));
     return STAN_OK;
 }

@@ -239,6 +239,7 @@ int solve_cholesky(stan_handle *h, stan_chol_report *rep);
 
 // recovery.cu
 int run_recovery(stan_handle *h, stan_recovery_stats *st);
+int recover_elements(stan_handle *h, const int32_t *d_list, int64_t count, double *d_strain, double *d_stress);
 
 // postprocess.cu
 int run_postprocess(stan_handle *h, double *ms);

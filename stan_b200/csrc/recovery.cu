@@ -25,12 +25,14 @@ __global__ void __launch_bounds__(REC_THREADS)
 k_recover(int64_t e_first, int64_t e_count, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
           const int32_t *__restrict__ node_index, const uint8_t *__restrict__ etype, const int32_t *__restrict__ emat,
           const double *__restrict__ lam_tab, const double *__restrict__ G_tab, const double *__restrict__ ufull,
-          double *__restrict__ strain, double *__restrict__ stress, int32_t *err) {
+          double *__restrict__ strain, double *__restrict__ stress, int32_t *err,
+          const int32_t *__restrict__ elem_list = nullptr) {
     __shared__ double s_val[REC_THREADS / 8][8][12];
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t el = t >> 3, e = e_first + el;       // local / global element index
+    const int64_t el = t >> 3;                         // local element index
     const int g = (int)(t & 7), le = threadIdx.x >> 3;
     const bool valid = el < e_count;
+    const int64_t e = !valid ? 0 : (elem_list ? (int64_t)elem_list[el] : e_first + el);   // global element index
     int type = STAN_HEX8_G2;
     if (valid) {
         type = etype[e];
@@ -139,6 +141,19 @@ static int upload_recovery_tables() {
             N[i * 8 + k] = 1.0 / 8.0 * (1 + S[k][0] * xi) * (1 + S[k][1] * eta) * (1 + S[k][2] * zeta);
     }
     STAN_CUDA(cudaMemcpyToSymbol(c_N, N, sizeof N));
+    return STAN_OK;
+}
+
+// strain/stress of an arbitrary element list (post-processing of a rank's nodes needs the elements
+// around them, wherever ElemLib puts them); same kernel, same arithmetic as run_recovery
+int recover_elements(stan_handle *h, const int32_t *d_list, int64_t count, double *d_strain, double *d_stress) {
+    cudaStream_t s = h->stream;
+    if (count <= 0) return STAN_OK;
+    k_recover<<<div_up(8 * count, REC_THREADS), REC_THREADS, 0, s>>>(
+        0, count, h->d_conn.p, h->d_xyz.p, h->d_node_index.p, h->d_etype.p, h->d_emat.p, h->d_lambda.p, h->d_G.p,
+        h->d_ufull.p, d_strain, d_stress, h->d_err.p, d_list);
+    STAN_CUDA(cudaGetLastError());
+    h->launches += 1;
     return STAN_OK;
 }
 

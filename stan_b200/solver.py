@@ -147,8 +147,10 @@ class Solver:
         """Part.Load_Scalar (Part.cs:231-528): returns (cell (n_elem,24,3) max/average/min, point (n_nodes,24), ms)."""
         ms = C.c_double()
         native.check(self._lib.stan_postprocess(self._h, C.byref(ms)))
-        cell = np.empty((self.model.n_elem, 24, 3), dtype=np.float32)
-        point = np.empty((self.model.n_nodes, 24), dtype=np.float32)
+        e0, e1 = self.element_range()
+        r0, r1 = self.partition()
+        cell = np.empty((e1 - e0, 24, 3), dtype=np.float32)
+        point = np.empty((r1 - r0, 24), dtype=np.float32)      # NodeLib order on one GPU, row order when partitioned
         native.check(self._lib.stan_get_scalars(self._h, _p(cell), _p(point)))
         return cell, point, ms.value
 
