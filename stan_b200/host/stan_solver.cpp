@@ -123,7 +123,9 @@ int linear_statics(stdb::Database &db, int device, bool strict) {
 
     stan_options opt = {device, 0, 1, 0};
     stan_handle *h = nullptr;
+    const double t_dev0 = now_s();
     if (stan_create(&opt, &h)) return fail("stan_create");
+    const double t_device_start = now_s() - t_dev0;               // CUDA context + module load: a fixed cost per process
     int rc = 0;
     std::vector<int32_t> node_index(nn);
     std::vector<double> U(3 * nn), strain((size_t)48 * ne), stress((size_t)48 * ne);
@@ -210,6 +212,7 @@ int linear_statics(stdb::Database &db, int device, bool strict) {
     db.analysis.present = true;
     db.analysis.result_stepno = 1;                                // Solver.cs:56
     printf("\n%s\n  Total CPU time: %.2f s\n%s\n", SEP, now_s() - t_start, SEP);   // Solver.cs:213-216
+    printf("   Device start-up (CUDA context, once per process): %.2f s\n", t_device_start);
     if (cholesky)
         printf("   Cholesky: skyline %.2f GB in %lld blocks of 64x64, factor %.2f ms (%.2f TFLOP/s), solves %.2f ms, "
                "assembly kernel %.2f ms, recovery %.2f ms\n", chol.skyline_bytes / 1e9, (long long)chol.n_blocks, chol.factor_ms,
