@@ -429,6 +429,7 @@ int solve_cholesky(stan_handle *h, stan_chol_report *rep) {
     auto free_all = [&]() { band.release(s); w.release(s); y.release(s); x.release(s); dF.release(s); dP.release(s); };
     if (band.alloc((size_t)total_blocks * CBB, s) != STAN_OK) {
         free_all();
+        (void)cudaGetLastError();                         // the failed allocation must not poison later calls
         set_error("stan_solve_cholesky: cannot allocate the %.1f GB skyline; use CG", band_bytes / 1e9);
         return STAN_E_NOMEM;
     }
