@@ -176,7 +176,7 @@ def run_ours(args):
         s.comm_init(uid[0])
     s.SetModel(m)
     t0 = time.perf_counter()
-    ni = s.AssignDOF()                                    # R0, host BFS (Database.cs:140-234); not in the step
+    ni = s.AssignDOF()                                    # R0 (Database.cs:140-234), device BFS at this size; not in the step
     t_dof = time.perf_counter() - t0
 
     call_wall = []                                        # host wall time of the three calls, per step
@@ -252,7 +252,7 @@ def run_ours(args):
                       "cg_iters_s": cg.iterationscount / (cg.solve_ms * 1e-3), "cg_solve_ms": cg.solve_ms,
                       "cg_iter_gbs": cg.iter_bytes * cg.iterationscount / (cg.solve_ms * 1e-3) / 1e9,
                       "spmv_gbs": achieved, "spmv_ms": spmv_ms, "recovery_el_s": m.n_elem / (rc.recover_ms * 1e-3),
-                      "recovery_gbs": rc.recover_bytes / (rc.recover_ms * 1e-3) / 1e9, "assign_dof_host_s": t_dof,
+                      "recovery_gbs": rc.recover_bytes / (rc.recover_ms * 1e-3) / 1e9, "assign_dof_s": t_dof,
                       "wall_ms_per_step": wall_ms, "call_wall_ms_max_over_ranks": call_ms},
         "roofline": {"kernel": "k_spmv (block-row CSR SpMV + p.Ap)", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

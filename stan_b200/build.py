@@ -15,7 +15,7 @@ OUT_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(OUT_DIR, "obj")
 LIB = os.path.join(OUT_DIR, "libstan_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["api.cu", "pattern.cu", "assembly.cu", "cg.cu", "cholesky.cu", "recovery.cu", "postprocess.cu", "comm.cu", "dofmap.cpp"]
+SOURCES = ["api.cu", "pattern.cu", "assembly.cu", "cg.cu", "cholesky.cu", "recovery.cu", "postprocess.cu", "comm.cu", "dofmap_gpu.cu", "dofmap.cpp"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler",
          "-fPIC,-fvisibility=hidden,-O2", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 

@@ -220,7 +220,16 @@ int stan_assign_dof(stan_handle *h, int32_t *node_index_out) {
     STAN_TRY(check(h));
     if (!h->have_mesh) { set_error("stan_assign_dof before stan_set_mesh"); return STAN_E_STATE; }
     std::vector<int32_t> ni((size_t)h->n_nodes);
-    STAN_TRY(assign_dof_host(h->n_nodes, h->n_elem, h->h_conn.data(), ni.data()));
+    // Same numbering either way (tested bit for bit).  The level-synchronous device traversal pays
+    // ~10 launches per BFS level, so it is for big meshes with wide levels; STAN_DOF=gpu|host forces one.
+    const char *mode = getenv("STAN_DOF");
+    bool on_device = mode ? !strcmp(mode, "gpu") : h->n_nodes >= 1000000;
+    if (on_device) {
+        bool narrow = false;
+        STAN_TRY(assign_dof_device(h, ni.data(), &narrow));
+        on_device = !narrow;
+    }
+    if (!on_device) STAN_TRY(assign_dof_host(h->n_nodes, h->n_elem, h->h_conn.data(), ni.data()));
     if (node_index_out) memcpy(node_index_out, ni.data(), ni.size() * sizeof(int32_t));
     return upload_dof_map(h, ni.data());
 }

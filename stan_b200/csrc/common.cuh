@@ -214,6 +214,9 @@ namespace stan {
 // dofmap.cpp
 int assign_dof_host(int64_t n_nodes, int64_t n_elem, const int32_t *conn, int32_t *node_index);
 
+// dofmap_gpu.cu
+int assign_dof_device(stan_handle *h, int32_t *node_index, bool *narrow);
+
 // pattern.cu
 int build_system_pattern(stan_handle *h);
 int build_rhs(stan_handle *h);
