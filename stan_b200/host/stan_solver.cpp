@@ -5,7 +5,7 @@
 // prints the console lines the reference prints, so the PrePost -> Solver -> PrePost workflow is
 // unchanged.  The reference's 10 s "Solver exit" sleep (Solver.cs:67-68) is not reproduced.
 //
-//   stan_solver model.STdb [-o out.STdb] [--strict] [--device N]
+//   stan_solver model.STdb [-o out.STdb] [--strict] [--device N] [--vtu PREFIX [--vtu-ascii]]
 //   stan_solver --roundtrip in.STdb out.STdb        decode + encode only (no GPU)
 //   stan_solver --import-bdf mesh.bdf out.STdb      Database.ReadNastranMesh (no GPU)
 //   stan_solver --dump in.STdb                      one-line JSON summary (no GPU)
@@ -21,6 +21,7 @@
 #include "../../include/stan_b200.h"
 #include "bdf.hpp"
 #include "stdb.hpp"
+#include "vtu.hpp"
 
 namespace {
 
@@ -76,7 +77,7 @@ int dump(const stdb::Database &db) {
 }
 
 // Solver.SolverLinearStatics through the C ABI.  Returns 0 on success.
-int linear_statics(stdb::Database &db, int device, bool strict) {
+int linear_statics(stdb::Database &db, int device, bool strict, const std::string &vtu_prefix, bool vtu_ascii) {
     const double t_start = now_s();
     const int64_t nn = (int64_t)db.nodes.size(), ne = (int64_t)db.elems.size();
     std::unordered_map<int32_t, int32_t> node_pos, mat_pos;
@@ -138,6 +139,7 @@ int linear_statics(stdb::Database &db, int device, bool strict) {
     memset(&rep, 0, sizeof rep);
     memset(&chol, 0, sizeof chol);
     const bool cholesky = db.analysis.present && db.analysis.linsolver == "Cholesky";   // Solver.cs:162-163
+    std::string vtu_written;
     do {
         if (stan_set_mesh(h, nn, xyz.data(), ne, conn.data(), etype.data(), emat.data())) { rc = fail("stan_set_mesh"); break; }
         if (stan_set_materials(h, (int32_t)E.size(), E.data(), nu.data())) { rc = fail("stan_set_materials"); break; }
@@ -181,6 +183,21 @@ int linear_statics(stdb::Database &db, int device, bool strict) {
         if (stan_recover(h, &rs)) { rc = fail("stan_recover"); break; }
         if (stan_get_displacements(h, U.data())) { rc = fail("stan_get_displacements"); break; }
         if (stan_get_strain_stress(h, strain.data(), stress.data())) { rc = fail("stan_get_strain_stress"); break; }
+        if (!vtu_prefix.empty()) {                                // PrePost's Export window (ExportWindow.xaml.cs:43-108)
+            std::vector<float> point((size_t)24 * nn);
+            std::vector<double> disp(3 * nn);
+            if (stan_postprocess(h, nullptr)) { rc = fail("stan_postprocess"); break; }
+            if (stan_get_scalars(h, nullptr, point.data())) { rc = fail("stan_get_scalars"); break; }
+            for (int64_t i = 0; i < nn; i++)
+                for (int d = 0; d < 3; d++) disp[3 * i + d] = U[3 * (int64_t)node_index[i] + d];
+            std::string path, verr;
+            if (!vtu::write_increment(db, disp, point, vtu_prefix, vtu_ascii, path, verr)) {
+                fprintf(stderr, "stan_solver: %s\n", verr.c_str());
+                rc = 2;
+                break;
+            }
+            vtu_written = path;
+        }
         printf("            Done\n");                             // :200
     } while (false);
     stan_destroy(h);
@@ -212,6 +229,7 @@ int linear_statics(stdb::Database &db, int device, bool strict) {
     db.analysis.present = true;
     db.analysis.result_stepno = 1;                                // Solver.cs:56
     printf("\n%s\n  Total CPU time: %.2f s\n%s\n", SEP, now_s() - t_start, SEP);   // Solver.cs:213-216
+    if (!vtu_written.empty()) printf("   Result file exported: %s\n", vtu_written.c_str());
     printf("   Device start-up (CUDA context, once per process): %.2f s\n", t_device_start);
     if (cholesky)
         printf("   Cholesky: skyline %.2f GB in %lld blocks of 64x64, factor %.2f ms (%.2f TFLOP/s), solves %.2f ms, "
@@ -253,13 +271,16 @@ int main(int argc, char **argv) {
         printf("{\"nodes\": %zu, \"elements\": %zu, \"import_errors\": %zu}\n", db.nodes.size(), db.elems.size(), rep.errors.size());
         return 0;
     }
-    if (argc < 2) { fprintf(stderr, "usage: stan_solver model.STdb [-o out.STdb] [--strict] [--device N]\n"); return 1; }
+    if (argc < 2) { fprintf(stderr, "usage: stan_solver model.STdb [-o out.STdb] [--strict] [--device N] [--vtu PREFIX [--vtu-ascii]]\n"); return 1; }
     std::string in = argv[1], out = argv[1];
-    bool strict = false;
+    bool strict = false, vtu_ascii = false;
+    std::string vtu_prefix;
     int device = -1;
     for (int i = 2; i < argc; i++) {
         if (!strcmp(argv[i], "-o") && i + 1 < argc) out = argv[++i];
         else if (!strcmp(argv[i], "--strict")) strict = true;
+        else if (!strcmp(argv[i], "--vtu") && i + 1 < argc) vtu_prefix = argv[++i];
+        else if (!strcmp(argv[i], "--vtu-ascii")) vtu_ascii = true;
         else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
     }
     banner();
@@ -276,7 +297,7 @@ int main(int argc, char **argv) {
         fprintf(stderr, "stan_solver: linear solver '%s' is not on the native path (CG and Cholesky are)\n", db.analysis.linsolver.c_str());
         return 3;
     }
-    int rc = linear_statics(db, device, strict);
+    int rc = linear_statics(db, device, strict, vtu_prefix, vtu_ascii);
     if (rc) return rc;
     if (!stdb::write_file(out, stdb::encode(db), err)) { fprintf(stderr, "stan_solver: %s\n", err.c_str()); return 2; }   // ExportOutput
     return 0;

@@ -67,3 +67,65 @@ def test_stan_solver_cli_cholesky(oracle, tmp_path):
     src.write_bytes(stdb.encode(stdb.from_model(m)))
     r = subprocess.run([host, str(src), "-o", str(out)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 3 and "LU" in r.stderr
+
+
+def _vtu_arrays(path):
+    """Minimal VTU reader for the two modes the writer produces (ascii, inline base64 with UInt32 headers)."""
+    import base64
+    import xml.etree.ElementTree as ET
+    root = ET.parse(path).getroot()
+    assert root.tag == "VTKFile" and root.get("type") == "UnstructuredGrid" and root.get("byte_order") == "LittleEndian"
+    piece = root.find("UnstructuredGrid/Piece")
+    dt = {"Float32": np.float32, "Int64": np.int64, "UInt8": np.uint8}
+    out = {"n_points": int(piece.get("NumberOfPoints")), "n_cells": int(piece.get("NumberOfCells")), "order": []}
+    for da in piece.iter("DataArray"):
+        t, text = dt[da.get("type")], da.text.strip()
+        if da.get("format") == "ascii":
+            a = np.array(text.split(), dtype=np.float64).astype(t)
+        else:
+            n = int(np.frombuffer(base64.b64decode(text[:8]), dtype=np.uint32)[0])
+            a = np.frombuffer(base64.b64decode(text[8:]), dtype=t)
+            assert a.nbytes == n
+        out[da.get("Name")] = a
+        out["order"].append(da.get("Name"))
+    return out
+
+
+@pytest.mark.parametrize("ascii_mode", [False, True])
+def test_stan_solver_cli_vtu_export(tmp_path, ascii_mode):
+    """`--vtu` writes what PrePost's Export window writes (ExportWindow.xaml.cs:43-108, Part.ExportGrid
+    Part.cs:857-939): per part its sorted node list as deformed points, hexahedra, nodal-averaged arrays."""
+    from stan_b200 import build
+    from stan_b200.solver import Solver
+    host = build.build_host()
+    m = mesh.beam(4, 3, 9, jitter=True, n_parts=3, tolerance=1e-10)
+    src, out, prefix = tmp_path / "model.STdb", tmp_path / "solved.STdb", tmp_path / "res"
+    src.write_bytes(stdb.encode(stdb.from_model(m)))
+    cmd = [host, str(src), "-o", str(out), "--strict", "--vtu", str(prefix)] + (["--vtu-ascii"] if ascii_mode else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "Result file exported" in r.stdout, r.stdout + r.stderr
+    v = _vtu_arrays(str(prefix) + "_001.vtu")
+    with Solver() as s:
+        res = s.SolverLinearStatics(m, merit_check=0)
+        _, point, _ = s.Load_Scalar()
+    # expected layout: parts in order of appearance, each with its ascending distinct nodes
+    pts, cells, srcs = [], [], []
+    for pid in (1, 2, 3):
+        el = np.where(m.elem_pid == pid)[0]
+        ids = np.unique(m.conn[el])
+        local = {int(n): len(srcs) + k for k, n in enumerate(ids)}
+        srcs.extend(ids.tolist())
+        cells.extend([[local[int(n)] for n in m.conn[e]] for e in el])
+    srcs = np.array(srcs)
+    assert v["n_points"] == len(srcs) > m.n_nodes and v["n_cells"] == m.n_elem      # interface nodes once per part
+    assert np.array_equal(v["connectivity"].reshape(-1, 8), np.array(cells))
+    assert np.array_equal(v["offsets"], 8 * np.arange(1, m.n_elem + 1)) and np.all(v["types"] == 12)
+    np.testing.assert_allclose(v["Points"].reshape(-1, 3), (m.xyz + res.disp)[srcs].astype(np.float32), rtol=2e-6, atol=1e-7)
+    names = ["Displacement X", "Displacement Y", "Displacement Z", "Total Displacement", "Stress XX", "Stress YY", "Stress ZZ",
+             "Stress XY", "Stress YZ", "Stress XZ", "Stress P1", "Stress P2", "Stress P3", "von Mises Stress", "Strain XX",
+             "Strain YY", "Strain ZZ", "Strain XY", "Strain YZ", "Strain XZ", "Strain P1", "Strain P2", "Strain P3",
+             "Effective Strain"]
+    assert v["order"][:24] == names[:4] + names[14:] + names[4:14]                   # Displacement, Strain, Stress
+    for k, name in enumerate(names):
+        scale = np.abs(point[:, k]).max() + 1e-30
+        assert np.abs(v[name] - point[srcs, k]).max() <= 2e-6 * scale, name
