@@ -73,7 +73,7 @@ CXX = "/usr/bin/g++"   # the image's $CXX wrapper lacks some specs; the system g
 def build_host(force: bool = False) -> str:
     """Native solver host (STdb codec, BDF import, console driver) linked against libstan_b200.so."""
     lib = build(force=False)
-    srcs = [os.path.join(HOST_SRC, f) for f in ("stan_solver.cpp", "stdb.cpp", "bdf.cpp", "vtu.cpp")]
+    srcs = [os.path.join(HOST_SRC, f) for f in ("stan_solver.cpp", "stdb.cpp", "bdf.cpp", "vtu.cpp", "model_build.cpp")]
     deps = srcs + [os.path.join(HOST_SRC, f) for f in os.listdir(HOST_SRC) if f.endswith(".hpp")] + [lib]
     if force or _stale(HOST_BIN, deps):
         cmd = [CXX, "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", HOST_BIN] + srcs + \

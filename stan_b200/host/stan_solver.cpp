@@ -8,6 +8,7 @@
 //   stan_solver model.STdb [-o out.STdb] [--strict] [--device N] [--vtu PREFIX [--vtu-ascii]]
 //   stan_solver --roundtrip in.STdb out.STdb        decode + encode only (no GPU)
 //   stan_solver --import-bdf mesh.bdf out.STdb      Database.ReadNastranMesh (no GPU)
+//   stan_solver --build mesh.bdf out.STdb [...]     import + materials / BC text / analysis settings (no GPU)
 //   stan_solver --dump in.STdb                      one-line JSON summary (no GPU)
 #include <chrono>
 #include <cmath>
@@ -20,6 +21,7 @@
 
 #include "../../include/stan_b200.h"
 #include "bdf.hpp"
+#include "model_build.hpp"
 #include "stdb.hpp"
 #include "vtu.hpp"
 
@@ -258,6 +260,49 @@ int main(int argc, char **argv) {
         stdb::Database db;
         if (!stdb::read_file(argv[2], bytes, err) || !stdb::decode(bytes, db, err)) { fprintf(stderr, "stan_solver: %s\n", err.c_str()); return 2; }
         return dump(db);
+    }
+    if (argc >= 2 && !strcmp(argv[1], "--build")) {               // the PrePost steps between import and solve, scripted
+        if (argc < 4) {
+            fprintf(stderr, "usage: stan_solver --build mesh.bdf out.STdb [--material E NU]... [--part-mat PID MATID]...\n"
+                            "       [--elem-type HEX8_G1|HEX8_G2] [--spc rows.txt]... [--load rows.txt]...\n"
+                            "       [--solver CG|Cholesky] [--tol T] [--itermax N]\n");
+            return 1;
+        }
+        stdb::Database db;
+        bdf::ImportReport rep;
+        if (!bdf::read_nastran_mesh(argv[2], db, rep, err)) { fprintf(stderr, "stan_solver: %s\n", err.c_str()); return 2; }
+        db.ndof = (int32_t)(3 * db.nodes.size());
+        std::string solver = "CG";
+        double tol = 1.0e-6;
+        int itermax = 0;
+        bool part_mat_given = false;
+        for (int i = 4; i < argc; i++) {
+            const std::string a = argv[i];
+            if (a == "--material" && i + 2 < argc) { model_build::add_material(db, atof(argv[i + 1]), atof(argv[i + 2])); i += 2; }
+            else if (a == "--part-mat" && i + 2 < argc) { model_build::set_part_material(db, atoi(argv[i + 1]), atoi(argv[i + 2])); part_mat_given = true; i += 2; }
+            else if (a == "--elem-type" && i + 1 < argc) { model_build::set_hex_type(db, -1, argv[++i]); }
+            else if ((a == "--spc" || a == "--load") && i + 1 < argc) {
+                std::string text;
+                if (!stdb::read_file(argv[++i], text, err)) { fprintf(stderr, "stan_solver: %s\n", err.c_str()); return 2; }
+                const bool spc = a == "--spc";
+                if (!model_build::add_bc(db, spc ? "SPC" : "PointLoad", spc ? "Fix" : "Load", model_build::parse_bc_text(text), err)) {
+                    fprintf(stderr, "stan_solver: %s\n", err.c_str());
+                    return 3;
+                }
+            }
+            else if (a == "--solver" && i + 1 < argc) solver = argv[++i];
+            else if (a == "--tol" && i + 1 < argc) tol = atof(argv[++i]);
+            else if (a == "--itermax" && i + 1 < argc) itermax = atoi(argv[++i]);
+            else { fprintf(stderr, "stan_solver: unknown or incomplete option '%s'\n", a.c_str()); return 1; }
+        }
+        if (!part_mat_given && !db.mats.empty()) model_build::set_part_material(db, -1, db.mats.front().id);
+        model_build::set_analysis(db, solver, tol, itermax);
+        if (!stdb::write_file(argv[3], stdb::encode(db), err)) { fprintf(stderr, "stan_solver: %s\n", err.c_str()); return 2; }
+        size_t rows = 0;
+        for (const auto &bc : db.bcs) rows += bc.nodal.size();
+        printf("{\"nodes\": %zu, \"elements\": %zu, \"import_errors\": %zu, \"materials\": %zu, \"bcs\": %zu, \"bc_rows\": %zu}\n",
+               db.nodes.size(), db.elems.size(), rep.errors.size(), db.mats.size(), db.bcs.size(), rows);
+        return 0;
     }
     if (argc >= 2 && !strcmp(argv[1], "--import-bdf")) {
         if (argc != 4) { fprintf(stderr, "usage: stan_solver --import-bdf mesh.bdf out.STdb\n"); return 1; }

@@ -100,3 +100,48 @@ def test_bdf_import_of_generated_mesh(host, tmp_path):
                    "GRID           2         7.11+15     5.0     0.0\nCTETRA         9       1       1       2       3       4\n")
     rep = json.loads(_run(host, "--import-bdf", str(bad), str(out)))
     assert rep == {"nodes": 1, "elements": 0, "import_errors": 2}
+
+
+def test_build_model_from_bdf_and_pasted_bc_text(host, tmp_path):
+    """`--build`: the PrePost steps between import and solve (README.md:50-76 of the reference) scripted —
+    materials (MainWindow.AddMat), part material / element type (BOX_Part), boundary conditions in the
+    Paste format with its quirks (BOX_BC.xaml.cs:228-270, BoundaryCondition.cs:87-98), Analysis settings."""
+    m = mesh.beam(3, 2, 5, n_parts=2)
+    bdf, out = tmp_path / "mesh.bdf", tmp_path / "model.STdb"
+    mesh.write_bdf(m, str(bdf))
+    spc = tmp_path / "spc.txt"
+    spc.write_text("1\t1\t1\t1\r\n2\t1\t0\t1\r\nnot a row\n3,1,1,0\n4 0 0 1\n9999\t1\t1\t1\n5\t1\t1\n6\t1e0\t1.0\t+1\n")
+    load = tmp_path / "load.txt"
+    load.write_text("70\t12.5\t0\t-3e2\n71\t0.5\t0\t0\n")
+    r = subprocess.run([host, "--build", str(bdf), str(out), "--material", "210000", "0.3", "--material", "70000", "0.33",
+                        "--part-mat", "1", "1", "--part-mat", "2", "2", "--elem-type", "HEX8_G1", "--spc", str(spc),
+                        "--load", str(load), "--solver", "Cholesky", "--tol", "1e-9", "--itermax", "500"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout)
+    assert info == {"nodes": m.n_nodes, "elements": m.n_elem, "import_errors": 0, "materials": 2, "bcs": 2, "bc_rows": 7}
+    db = stdb.decode(out.read_bytes())
+    assert [(x.id, x.type, x.name, x.E, x.poisson, x.colorid) for x in db.mats] == \
+        [(1, "Elastic", "New Material", 210000.0, 0.3, 1), (2, "Elastic", "New Material", 70000.0, 0.33, 2)]
+    assert all(e.type == "HEX8_G1" for e in db.elems)
+    assert [e.matid for e in db.elems] == [int(p) for p in m.elem_pid]             # part 1 -> material 1, part 2 -> 2
+    (k1, fix), (k2, ld) = db.bcs
+    assert (k1, fix.id, fix.type, fix.colorid, k2, ld.id, ld.type, ld.colorid) == (1, 1, "SPC", 1, 2, 2, "PointLoad", 2)
+    # tab, comma and space rows are read; CRLF tolerated; malformed / 3-field / unknown-node rows are dropped
+    assert [(n, v.M, v.rows, v.cols) for n, v in fix.nodal] == \
+        [(1, [1.0, 1.0, 1.0], 3, 1), (2, [1.0, 0.0, 1.0], 3, 1), (3, [1.0, 1.0, 0.0], 3, 1), (4, [0.0, 0.0, 1.0], 3, 1),
+         (6, [1.0, 1.0, 1.0], 3, 1)]
+    assert [(n, v.M) for n, v in ld.nodal] == [(70, [12.5, 0.0, -300.0]), (71, [0.5, 0.0, 0.0])]
+    a = db.analysis
+    assert (a.type, a.linsolver, a.tolerance, a.itermax, a.result_stepno) == ("Linear_Statics", "Cholesky", 1e-9, 500, 0)
+    assert db.ndof == m.n_dof
+    # a single pasted line is ignored like the reference's `text.Length > 1`; a repeated node is its Dictionary.Add failure
+    one = tmp_path / "one.txt"
+    one.write_text("1\t1\t1\t1")
+    r = subprocess.run([host, "--build", str(bdf), str(out), "--spc", str(one)], capture_output=True, text=True)
+    assert r.returncode == 0 and json.loads(r.stdout)["bc_rows"] == 0
+    assert stdb.decode(out.read_bytes()).analysis.linsolver == "CG" and stdb.decode(out.read_bytes()).analysis.tolerance == 1e-6
+    dup = tmp_path / "dup.txt"
+    dup.write_text("1\t1\t1\t1\n1\t0\t0\t0\n")
+    r = subprocess.run([host, "--build", str(bdf), str(out), "--spc", str(dup)], capture_output=True, text=True)
+    assert r.returncode == 3 and "listed twice" in r.stderr

@@ -2,7 +2,7 @@
 3 parts, CG with tolerance 1e-6 and no iteration limit — images/Solver.PNG, images/Properties.png) is
 not in the checkout, so a generated mesh of the same size class runs the same workflow end to end:
 
-    BDF text -> `stan_solver --import-bdf` -> STdb (+ materials / SPC / loads, as PrePost would add them)
+    BDF text + pasted BC rows -> `stan_solver --build` -> STdb (materials, part properties, SPC / loads, analysis)
             -> `stan_solver model.STdb` (GPU, reference defaults incl. ALGLIB's energy-functional stop)
             -> STdb with results
 
@@ -29,15 +29,26 @@ from stan_b200 import build, mesh, stdb  # noqa: E402
 work = sys.argv[1] if len(sys.argv) > 1 else tempfile.mkdtemp(prefix="example1_")
 host = build.build_host()
 m = mesh.beam(15, 15, 51, n_parts=3, tolerance=1e-6, max_iter=0)           # 11 475 elements, 13 312 nodes
-bdf, raw, model, solved = (os.path.join(work, f) for f in ("mesh.bdf", "mesh.STdb", "model.STdb", "solved.STdb"))
+bdf, model, solved = (os.path.join(work, f) for f in ("mesh.bdf", "model.STdb", "solved.STdb"))
+spc_txt, load_txt = os.path.join(work, "spc.txt"), os.path.join(work, "load.txt")
 mesh.write_bdf(m, bdf)
-r = subprocess.run([host, "--import-bdf", bdf, raw], capture_output=True, text=True, timeout=600)
+with open(spc_txt, "w") as fh:                                              # the 4-column paste format of README.md:55
+    fh.writelines(f"{n + 1}\t{v[0]:g}\t{v[1]:g}\t{v[2]:g}\n" for n, v in zip(m.spc_node, m.spc_val))
+with open(load_txt, "w") as fh:
+    fh.writelines(f"{n + 1}\t{v[0]!r}\t{v[1]!r}\t{v[2]!r}\n" for n, v in zip(m.load_node, m.load_val.tolist()))
+cmd = [host, "--build", bdf, model, "--spc", spc_txt, "--load", load_txt, "--tol", "1e-6"]
+for E, nu in zip(m.mat_E, m.mat_nu):
+    cmd += ["--material", repr(float(E)), repr(float(nu))]
+for pid in sorted(set(m.elem_pid.tolist())):                                # parts alternate between the two materials
+    cmd += ["--part-mat", str(pid), str(int(m.elem_mat[m.elem_pid == pid][0]) + 1)]
+r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
 assert r.returncode == 0, r.stderr
 imported = json.loads(r.stdout)
-db = stdb.decode(open(raw, "rb").read())                                    # what the importer produced
-full = stdb.from_model(m)                                                   # + materials, BCs, analysis (PrePost's job)
+db = stdb.decode(open(model, "rb").read())                                  # what the native builder produced ...
+full = stdb.from_model(m)                                                   # ... is the model the Python side describes
 assert [n.id for n in db.nodes] == [n.id for n in full.nodes] and [e.nlist for e in db.elems] == [e.nlist for e in full.elems]
-open(model, "wb").write(stdb.encode(full))
+assert [e.matid for e in db.elems] == [e.matid for e in full.elems] and [(x.E, x.poisson) for x in db.mats] == [(x.E, x.poisson) for x in full.mats]
+assert [[(n, v.M) for n, v in bc.nodal] for _, bc in db.bcs] == [[(n, v.M) for n, v in bc.nodal] for _, bc in full.bcs]
 
 t0 = time.perf_counter()
 r = subprocess.run([host, model, "-o", solved], capture_output=True, text=True, timeout=600)
