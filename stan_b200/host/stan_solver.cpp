@@ -261,6 +261,16 @@ int main(int argc, char **argv) {
         if (!stdb::read_file(argv[2], bytes, err) || !stdb::decode(bytes, db, err)) { fprintf(stderr, "stan_solver: %s\n", err.c_str()); return 2; }
         return dump(db);
     }
+    if (argc >= 2 && !strcmp(argv[1], "--remove-results")) {      // MainWindow.RemoveResults_Click (MainWindow.xaml.cs:731-763)
+        if (argc != 4) { fprintf(stderr, "usage: stan_solver --remove-results in.STdb out.STdb\n"); return 1; }
+        stdb::Database db;
+        if (!stdb::read_file(argv[2], bytes, err) || !stdb::decode(bytes, db, err)) { fprintf(stderr, "stan_solver: %s\n", err.c_str()); return 2; }
+        db.analysis.result_stepno = 0;                            // AnalysisLib.SetResultStepNo(0)
+        for (auto &e : db.elems) { e.strain.clear(); e.stress.clear(); }          // Element.ClearResults: Stress = Strain = null
+        for (auto &n : db.nodes) { n.dispx = {0.0}; n.dispy = {0.0}; n.dispz = {0.0}; }   // Node.Initialize_StepZero
+        if (!stdb::write_file(argv[3], stdb::encode(db), err)) { fprintf(stderr, "stan_solver: %s\n", err.c_str()); return 2; }
+        return 0;
+    }
     if (argc >= 2 && !strcmp(argv[1], "--build")) {               // the PrePost steps between import and solve, scripted
         if (argc < 4) {
             fprintf(stderr, "usage: stan_solver --build mesh.bdf out.STdb [--material E NU]... [--part-mat PID MATID]...\n"

@@ -145,3 +145,28 @@ def test_build_model_from_bdf_and_pasted_bc_text(host, tmp_path):
     dup.write_text("1\t1\t1\t1\n1\t0\t0\t0\n")
     r = subprocess.run([host, "--build", str(bdf), str(out), "--spc", str(dup)], capture_output=True, text=True)
     assert r.returncode == 3 and "listed twice" in r.stderr
+
+
+def test_remove_results(host, tmp_path):
+    """MainWindow.RemoveResults_Click (MainWindow.xaml.cs:731-763): Result_StepNo = 0, Element.ClearResults,
+    Node.Initialize_StepZero; numbering and everything else stays."""
+    m = mesh.beam(2, 2, 3)
+    db = stdb.from_model(m)
+    for k, n in enumerate(db.nodes):
+        n.dof = [3 * k, 3 * k + 1, 3 * k + 2]; n.elist = [1]
+        n.dispx, n.dispy, n.dispz = [0.0, 0.5 * k], [0.0, -1.0], [0.0, 2.0]
+    z = stdb.MatrixST([0.0] * 48, 8, 6)
+    for e in db.elems:
+        e.strain = [z, stdb.MatrixST([1e-3] * 48, 8, 6)]; e.stress = [z, stdb.MatrixST([210.0] * 48, 8, 6)]
+    db.analysis.result_stepno = 1
+    src, out = tmp_path / "solved.STdb", tmp_path / "clean.STdb"
+    src.write_bytes(stdb.encode(db))
+    r = subprocess.run([host, "--remove-results", str(src), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.stat().st_size < src.stat().st_size / 2
+    c = stdb.decode(out.read_bytes())
+    assert c.analysis.result_stepno == 0 and c.analysis.tolerance == db.analysis.tolerance
+    assert all(not e.strain and not e.stress for e in c.elems)
+    assert all(n.dispx == [0.0] and n.dispy == [0.0] and n.dispz == [0.0] for n in c.nodes)
+    assert [n.dof for n in c.nodes] == [n.dof for n in db.nodes] and [e.nlist for e in c.elems] == [e.nlist for e in db.elems]
+    assert [[(n, v.M) for n, v in bc.nodal] for _, bc in c.bcs] == [[(n, v.M) for n, v in bc.nodal] for _, bc in db.bcs]
