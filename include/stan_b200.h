@@ -102,8 +102,8 @@ typedef struct {
     int64_t skyline_bytes;     /* device bytes of the factor */
     double  flops;             /* flops of the factorisation as executed (dense blocks) */
     double  setup_ms;          /* envelope + CRS -> skyline (sparseconverttosks) */
-    double  factor_ms;         /* sparsecholeskyskyline */
-    double  solve_ms;          /* sparsecholeskysolvesks: two triangular solves */
+    double  factor_ms;         /* sparsecholeskyskyline, with U^T y = b carried along as one more column */
+    double  solve_ms;          /* sparsecholeskysolvesks: the remaining back substitution U x = y */
     int64_t kernel_launches;
 } stan_chol_report;
 

@@ -7,8 +7,9 @@
 // contiguous range K..E[K].  Factorisation A = U^T U is right-looking over block rows:
 //     panel(K):   U_KK = chol(A_KK);  U_KJ = U_KK^-T A_KJ          for J in (K, E[K]]
 //     update(K):  A_IJ -= U_KI^T U_KJ                              for K < I <= J <= E[K]
-// which is FP64-FMA bound (n * bandwidth^2 flops), not HBM bound like the CG path.  The triangular
-// solves U^T y = b and U x = y walk the same blocks once each.  SPC-fixed DOFs stay in the system as
+// which is FP64-FMA bound (n * bandwidth^2 flops), not HBM bound like the CG path.  U^T y = b is
+// carried through the factorisation as one more column; U x = y is one sweep over the block columns
+// in descending order.  SPC-fixed DOFs stay in the system as
 // identity rows (as in the CG path), so eliminating them only adds exact zeros; the tail of the last
 // block is padded with identity rows.  Every sum has a fixed order, so results are reproducible.
 // Single GPU: a skyline that does not fit one device is beyond what a direct solver is for here.
@@ -91,10 +92,15 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // 2016-FMA substitution, U_KK reads are shared-memory broadcasts, diagonals enter as reciprocals.
 // `tiles` (1, 2 or 4) quarters of a CTA take a block each: one per CTA while the row is short, so the
 // substitutions spread over the SMs instead of sharing one FP64 pipe.
-__global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, int tiles, int *__restrict__ err) {
+// The right-hand side rides along as one more column of the matrix (U^T y = b): warp 7 substitutes
+// y_K = U_KK^-T w_K, and the thread that holds column c of the solved block U_KJ subtracts its dot
+// product with y_K from w_J[c] — one owner per entry, fixed order — so no forward sweep is needed.
+__global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, int tiles, double *__restrict__ w,
+                                                       double *__restrict__ y, int *__restrict__ err) {
     __shared__ double D[CBB];
     __shared__ double rowbuf[2][CB];
     __shared__ double rinv[CB];
+    __shared__ double ys[CB];
     const int tid = threadIdx.x;
     const int c = tid & 63, rq = tid >> 6;
     pdl_trigger();
@@ -134,20 +140,49 @@ __global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, 
             if ((i >> 6) <= (i & 63)) gkk[i] = D[i];
     __syncthreads();
 
-    const int jt = blockIdx.x * tiles + rq;
-    if (rq >= tiles || jt >= m) return;
-    double *g = B.blk(K, K + 1 + jt);
-    double t[CB];
-#pragma unroll
-    for (int r = 0; r < CB; r++) t[r] = g[r * CB + c];
-#pragma unroll
-    for (int r = 0; r < CB; r++) {
-        t[r] = t[r] * rinv[r];
-#pragma unroll
-        for (int r2 = r + 1; r2 < CB; r2++) t[r2] -= D[r * CB + r2] * t[r];
+    if (tid >= 224) {                                     // warp 7: forward substitution of the right-hand side
+        const int lane = tid & 31;
+        double v0 = w[(int64_t)K * CB + lane], v1 = w[(int64_t)K * CB + lane + 32];
+        const double ri0 = rinv[lane], ri1 = rinv[lane + 32];
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+            const double yr = __shfl_sync(0xffffffffu, v0 * ri0, r);
+            if (lane == r) v0 = yr;
+            if (lane > r) v0 -= D[r * CB + lane] * yr;
+            v1 -= D[r * CB + lane + 32] * yr;
+        }
+#pragma unroll 8
+        for (int r = 32; r < CB; r++) {
+            const double yr = __shfl_sync(0xffffffffu, v1 * ri1, r - 32);
+            if (lane + 32 == r) v1 = yr;
+            if (lane + 32 > r) v1 -= D[r * CB + lane + 32] * yr;
+        }
+        ys[lane] = v0; ys[lane + 32] = v1;
+        if (blockIdx.x == 0) { y[(int64_t)K * CB + lane] = v0; y[(int64_t)K * CB + lane + 32] = v1; }
     }
+    const int jt = blockIdx.x * tiles + rq;
+    const bool active = rq < tiles && jt < m;
+    double t[CB];
+    if (active) {
+        double *g = B.blk(K, K + 1 + jt);
 #pragma unroll
-    for (int r = 0; r < CB; r++) g[r * CB + c] = t[r];
+        for (int r = 0; r < CB; r++) t[r] = g[r * CB + c];
+#pragma unroll
+        for (int r = 0; r < CB; r++) {
+            t[r] = t[r] * rinv[r];
+#pragma unroll
+            for (int r2 = r + 1; r2 < CB; r2++) t[r2] -= D[r * CB + r2] * t[r];
+        }
+#pragma unroll
+        for (int r = 0; r < CB; r++) g[r * CB + c] = t[r];
+    }
+    __syncthreads();                                      // y_K is in shared memory
+    if (active) {
+        double dot = 0.0;
+#pragma unroll
+        for (int r = 0; r < CB; r++) dot += t[r] * ys[r];
+        w[(int64_t)(K + 1 + jt) * CB + c] -= dot;
+    }
 }
 
 // ---- trailing update: C_IJ -= U_KI^T U_KJ ----------------------------------------------------
@@ -245,61 +280,6 @@ __global__ void __launch_bounds__(128) k_chol_update(BandDev B, int K, int m, in
     __syncthreads();
     pdl_wait();
     update_strip(B, K, m, ch, blockIdx.y, blockIdx.x, sm, bar);
-}
-
-// ---- U^T y = b, block row K: y_K = U_KK^-T w_K, then w_J -= U_KJ^T y_K for J in (K, E[K]] -------
-// The factor is final, so the diagonal block and this CTA's off-diagonal block are fetched before
-// pdl_wait(); only w_K depends on the previous step.  Substitution by one warp (2 entries per lane),
-// diagonals as reciprocals computed up front, so the 64-step chain is shuffle + multiply + FMA.
-__global__ void __launch_bounds__(256) k_chol_fwd(BandDev B, int K, int m, double *__restrict__ w,
-                                                  double *__restrict__ y) {
-    __shared__ double D[CBB];
-    __shared__ double ys[CB];
-    __shared__ double part[4][CB];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int c = tid & 63, q = tid >> 6;
-    pdl_trigger();
-    const double *gkk = B.blk(K, K);
-#pragma unroll
-    for (int i = 0; i < CBB / 256; i++) D[tid + 256 * i] = gkk[tid + 256 * i];
-    const bool has = (int)blockIdx.x < m;
-    const int J = K + 1 + blockIdx.x;
-    double gt[16];
-    if (has) {
-        const double *g = B.blk(K, J);
-#pragma unroll
-        for (int i = 0; i < 16; i++) gt[i] = g[(q * 16 + i) * CB + c];
-    }
-    pdl_wait();
-    if (tid < CB) ys[tid] = w[(int64_t)K * CB + tid];
-    __syncthreads();
-    if (tid < 32) {
-        double v0 = ys[lane], v1 = ys[lane + 32];
-        const double ri0 = 1.0 / D[lane * CB + lane], ri1 = 1.0 / D[(lane + 32) * CB + lane + 32];
-#pragma unroll 8
-        for (int r = 0; r < 32; r++) {
-            const double yr = __shfl_sync(0xffffffffu, v0 * ri0, r);
-            if (lane == r) v0 = yr;
-            if (lane > r) v0 -= D[r * CB + lane] * yr;
-            v1 -= D[r * CB + lane + 32] * yr;
-        }
-#pragma unroll 8
-        for (int r = 32; r < CB; r++) {
-            const double yr = __shfl_sync(0xffffffffu, v1 * ri1, r - 32);
-            if (lane + 32 == r) v1 = yr;
-            if (lane + 32 > r) v1 -= D[r * CB + lane + 32] * yr;
-        }
-        ys[lane] = v0; ys[lane + 32] = v1;
-    }
-    __syncthreads();
-    if (blockIdx.x == 0 && tid < CB) y[(int64_t)K * CB + tid] = ys[tid];
-    if (!has) return;
-    double p = 0.0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) p += gt[i] * ys[q * 16 + i];
-    part[q][c] = p;
-    __syncthreads();
-    if (q == 0) w[(int64_t)J * CB + c] -= ((part[0][c] + part[1][c]) + part[2][c]) + part[3][c];
 }
 
 // ---- U x = y, block column J (descending): x_J = U_JJ^-1 y_J, then y_I -= U_IJ x_J for I in [F[J], J) ----
@@ -460,7 +440,7 @@ int solve_cholesky(stan_handle *h, stan_chol_report *rep) {
         const int m = E[K] - (int)K;
         const int tiles = m > 2 * h->sm_count ? 4 : m > h->sm_count ? 2 : 1;
         STAN_CUDA(launch_step(k_chol_panel, dim3(std::max(1, div_up(m, tiles))), dim3(256), 0, s, use_pdl && K > 0,
-                              B, (int)K, m, tiles, h->d_err.p));
+                              B, (int)K, m, tiles, w.p, y.p, h->d_err.p));
         launches++;
         flops += b3 / 3 + (double)m * b3;
         if (m > 0) {
@@ -474,18 +454,14 @@ int solve_cholesky(stan_handle *h, stan_chol_report *rep) {
     }
     STAN_CUDA(cudaEventRecord(h->ev2, s));
 
-    // ---- triangular solves ----
+    // ---- back substitution (U^T y = b was carried through the factorisation) ----
     // the first sweep kernel must see the finished factor before its prologue: no early start for it
-    for (int64_t K = 0; K < nbk; K++) {
-        const int m = E[K] - (int)K;
-        STAN_CUDA(launch_step(k_chol_fwd, dim3(std::max(1, m)), dim3(256), 0, s, use_pdl && K > 0, B, (int)K, m, w.p, y.p));
-    }
     for (int64_t J = nbk - 1; J >= 0; J--) {
         const int cnt = (int)J - F[J];
         STAN_CUDA(launch_step(k_chol_bwd, dim3(std::max(1, cnt)), dim3(256), 0, s, use_pdl && J < nbk - 1, B, (int)J, cnt,
                               y.p, x.p));
     }
-    launches += 2 * nbk;
+    launches += nbk;
     STAN_CUDA(cudaEventRecord(h->ev3, s));
     STAN_CUDA(cudaGetLastError());
 
