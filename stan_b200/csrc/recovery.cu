@@ -21,19 +21,33 @@ __constant__ double c_N[8][8];       // N[i][g], HEX8_ShapeFunctions(node i, 1/s
 
 constexpr int REC_THREADS = 128;     // 16 elements per CTA
 
-__global__ void __launch_bounds__(REC_THREADS)
+__global__ void __launch_bounds__(REC_THREADS, 4)
 k_recover(int64_t e_first, int64_t e_count, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
           const int32_t *__restrict__ node_index, const uint8_t *__restrict__ etype, const int32_t *__restrict__ emat,
           const double *__restrict__ lam_tab, const double *__restrict__ G_tab, const double *__restrict__ ufull,
           double *__restrict__ strain, double *__restrict__ stress, int32_t *err,
           const int32_t *__restrict__ elem_list = nullptr) {
-    __shared__ double s_val[REC_THREADS / 8][8][12];
+    // 13-double rows: with 12 the four elements of a warp (96-double stride) sat on the same banks and
+    // every extrapolation read was a 4-way conflict (ncu: 359 M shared bank conflicts at 10M elements)
+    __shared__ double s_val[REC_THREADS / 8][8][13];
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t el = t >> 3;                         // local element index
     const int g = (int)(t & 7), le = threadIdx.x >> 3;
     const bool valid = el < e_count;
     const int64_t e = !valid ? 0 : (elem_list ? (int64_t)elem_list[el] : e_first + el);   // global element index
     int type = STAN_HEX8_G2;
+    // the 8 threads of an element fetch one node each (coordinates and displacement, Element.cs:214-221)
+    // and share them through shared memory; 49-double stride keeps the 4 elements of a warp on distinct banks
+    __shared__ double s_xu[REC_THREADS / 8][49];
+    if (valid) {
+        const int32_t nd = conn[8 * e + g];
+        const double *p = xyz + 3 * (int64_t)nd;
+        const double *u = ufull + 3 * (int64_t)node_index[nd];
+        double *d = s_xu[le];
+        d[3 * g] = p[0]; d[3 * g + 1] = p[1]; d[3 * g + 2] = p[2];
+        d[24 + 3 * g] = u[0]; d[24 + 3 * g + 1] = u[1]; d[24 + 3 * g + 2] = u[2];
+    }
+    __syncthreads();
     if (valid) {
         type = etype[e];
         double val[12];
@@ -41,17 +55,9 @@ k_recover(int64_t e_first, int64_t e_count, const int32_t *__restrict__ conn, co
         for (int c = 0; c < 12; c++) val[c] = 0.0;
         if (type == STAN_HEX8_G2 || g == 0) {
             const int gp = (type == STAN_HEX8_G2) ? g : 8;
-            const int4 c0 = *reinterpret_cast<const int4 *>(conn + 8 * e);
-            const int4 c1 = *reinterpret_cast<const int4 *>(conn + 8 * e + 4);
-            const int nd[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
             double X[24], U[24];
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const double *p = xyz + 3 * (int64_t)nd[k];
-                const double *u = ufull + 3 * (int64_t)node_index[nd[k]];   // Element.cs:214-221
-                X[3 * k] = p[0]; X[3 * k + 1] = p[1]; X[3 * k + 2] = p[2];
-                U[3 * k] = u[0]; U[3 * k + 1] = u[1]; U[3 * k + 2] = u[2];
-            }
+            for (int k = 0; k < 24; k++) { X[k] = s_xu[le][k]; U[k] = s_xu[le][24 + k]; }
             double J[9];
 #pragma unroll
             for (int r = 0; r < 3; r++)
