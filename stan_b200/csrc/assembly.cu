@@ -224,7 +224,7 @@ __constant__ unsigned char c_blk_i[36], c_blk_j[36];
 
 __device__ __forceinline__ int upper_index(int i, int j) { return i * 8 - (i * (i - 1)) / 2 + (j - i); }   // i <= j
 
-__global__ void __launch_bounds__(KB_THREADS)
+__global__ void __launch_bounds__(KB_THREADS, 3)
 k_hex8_ke_batch(int64_t n_local, const int32_t *__restrict__ lelem, const int32_t *__restrict__ conn,
                 const double *__restrict__ xyz, const uint8_t *__restrict__ etype, const int32_t *__restrict__ emat,
                 const double *__restrict__ lam_tab, const double *__restrict__ G_tab, double *__restrict__ ke_store,
