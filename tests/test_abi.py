@@ -56,3 +56,52 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower() or f == "build.py", f"{f} mentions the oracle"
+
+
+def _header_structs():
+    """typedef struct { ... } name;  ->  {name: [(ctype, field), ...]} from include/stan_b200.h."""
+    text = open(os.path.join(ROOT, "include", "stan_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for body, name in re.findall(r"typedef struct \{(.*?)\}\s*(stan_[a-z_]+);", text, flags=re.S):
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                t, names = decl.split(None, 1)
+                fields += [(t, n.strip()) for n in names.split(",")]
+        out[name] = fields
+    return out
+
+
+def test_ctypes_structs_mirror_the_header_field_by_field():
+    ct = {"int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double}
+    pairs = {"stan_options": native.Options, "stan_cg_options": native.CgOptions, "stan_cg_report": native.CgReport,
+             "stan_assembly_stats": native.AssemblyStats, "stan_chol_report": native.CholReport,
+             "stan_recovery_stats": native.RecoveryStats}
+    hs = _header_structs()
+    assert set(hs) == set(pairs)
+    for name, cls in pairs.items():
+        assert [(n, t) for n, t in cls._fields_] == [(f, ct[t]) for t, f in hs[name]], name
+    assert C.sizeof(native.CholReport) == 72
+
+
+def test_csharp_shim_binds_declared_symbols_with_matching_structs():
+    """interop/StanNative.cs is source only (no .NET here): at least keep it consistent with the header."""
+    cs = open(os.path.join(ROOT, "interop", "StanNative.cs")).read()
+    declared = set(_declared_symbols())
+    imported = set(re.findall(r"static extern \w+ (stan_[a-z0-9_]+)\(", cs))
+    assert imported and imported <= declared, imported - declared
+    assert {"stan_assemble", "stan_solve_cg", "stan_solve_cholesky", "stan_recover", "stan_get_displacements",
+            "stan_get_strain_stress"} <= imported
+    hs = _header_structs()
+    cs_structs = {"Options": "stan_options", "CgOptions": "stan_cg_options", "CgReport": "stan_cg_report",
+                  "AssemblyStats": "stan_assembly_stats", "CholReport": "stan_chol_report", "RecoveryStats": "stan_recovery_stats"}
+    cs_type = {"int": "int32_t", "long": "int64_t", "double": "double"}
+    for cs_name, h_name in cs_structs.items():
+        m = re.search(r"internal struct %s\s*\{(.*?)\}" % cs_name, cs, flags=re.S)
+        assert m, cs_name
+        fields = []
+        for t, names in re.findall(r"public (int|long|double) ([^;]+);", m.group(1)):
+            fields += [(cs_type[t], n.strip()) for n in names.split(",")]
+        assert fields == hs[h_name], cs_name
