@@ -219,6 +219,8 @@ k_assemble_rows(int64_t nloc, int64_t row0, const int32_t *__restrict__ inc_ptr,
 //                    transpose of (j, i)) — fixed order, no atomics, every stored value written once,
 //                    coalesced.  The incidence list is the element-to-slot map.
 constexpr int KB_ELEMS = 8;                       // elements per CTA
+constexpr int KE_BLK = 10;                        // doubles per stored 3x3 block: 9 values + 1 pad = 80 B, 16-byte aligned
+constexpr int KE_ELEM = 36 * KE_BLK;              // doubles per element in the Ke store
 constexpr int KB_THREADS = KB_ELEMS * 36;         // one thread per upper block in phase 2
 __constant__ unsigned char c_blk_i[36], c_blk_j[36];
 
@@ -306,9 +308,10 @@ k_hex8_ke_batch(int64_t n_local, const int32_t *__restrict__ lelem, const int32_
             K[3 * a + a] += sdot;
         }
     }
-    double *out = ke_store + (le * 36 + blk) * 9;
+    double *out = ke_store + (le * 36 + blk) * KE_BLK;     // 80-byte slots: 16-byte aligned vector stores / loads
 #pragma unroll
-    for (int q = 0; q < 9; q++) out[q] = K[q];
+    for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2 *>(out + q) = make_double2(K[q], K[q + 1]);
+    out[8] = K[8];
 }
 
 constexpr int GA_WARPS = 8;
@@ -354,7 +357,7 @@ k_assemble_gather(int64_t nloc, int64_t row0, const int32_t *__restrict__ inc_pt
                         if (__shfl_sync(0xffffffffu, qj_mine, j) == myq) m |= 1 << j;
                     bits[u] = have ? m : 0;
                     irow[u] = ent & 7;
-                    blk[u] = ke_store + (int64_t)(g2l ? g2l[e] : e) * 324;
+                    blk[u] = ke_store + (int64_t)(g2l ? g2l[e] : e) * KE_ELEM;
                 }
             }
             double v[GA_GROUP][9];
@@ -362,9 +365,13 @@ k_assemble_gather(int64_t nloc, int64_t row0, const int32_t *__restrict__ inc_pt
             for (int u = 0; u < GA_GROUP; u++) {
                 if (bits[u]) {
                     const int j = __ffs(bits[u]) - 1, i = irow[u];
-                    const double *src = blk[u] + (i <= j ? upper_index(i, j) : upper_index(j, i)) * 9;
+                    const double *src = blk[u] + (i <= j ? upper_index(i, j) : upper_index(j, i)) * KE_BLK;
 #pragma unroll
-                    for (int q = 0; q < 9; q++) v[u][q] = src[q];
+                    for (int q = 0; q < 8; q += 2) {
+                        const double2 t2 = *reinterpret_cast<const double2 *>(src + q);
+                        v[u][q] = t2.x; v[u][q + 1] = t2.y;
+                    }
+                    v[u][8] = src[8];
                 }
             }
 #pragma unroll
@@ -386,7 +393,7 @@ k_assemble_gather(int64_t nloc, int64_t row0, const int32_t *__restrict__ inc_pt
                     while (rest) {                  // degenerate element: the node appears again at column j
                         j = __ffs(rest) - 1;
                         rest &= rest - 1;
-                        const double *src = blk[u] + (i <= j ? upper_index(i, j) : upper_index(j, i)) * 9;
+                        const double *src = blk[u] + (i <= j ? upper_index(i, j) : upper_index(j, i)) * KE_BLK;
                         for (int a = 0; a < 3; a++)
                             for (int b = 0; b < 3; b++) acc[3 * a + b] += (i <= j) ? src[3 * a + b] : src[3 * b + a];
                     }
@@ -512,13 +519,13 @@ static int run_assembly_two_kernel(stan_handle *h) {
         h->launches += 3;
     }
     size_t free_b = 0, total_b = 0;
-    const size_t need = (size_t)n_local * 324 * sizeof(double);
+    const size_t need = (size_t)n_local * KE_ELEM * sizeof(double);
     cudaMemGetInfo(&free_b, &total_b);
     if (h->d_ke.n * sizeof(double) < need && need + ((size_t)2 << 30) > free_b) {   // would not fit next to the matrix
         g2l.release(s); lelem.release(s);
         return 1;
     }
-    STAN_TRY(h->d_ke.alloc((size_t)n_local * 324, s));
+    STAN_TRY(h->d_ke.alloc((size_t)n_local * KE_ELEM, s));
     k_hex8_ke_batch<<<div_up(n_local, KB_ELEMS), KB_THREADS, 0, s>>>(n_local, h->world > 1 ? lelem.p : nullptr, h->d_conn.p,
                                                                     h->d_xyz.p, h->d_etype.p, h->d_emat.p, h->d_lambda.p,
                                                                     h->d_G.p, h->d_ke.p, h->d_err.p);
