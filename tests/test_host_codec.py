@@ -170,3 +170,42 @@ def test_remove_results(host, tmp_path):
     assert all(n.dispx == [0.0] and n.dispy == [0.0] and n.dispz == [0.0] for n in c.nodes)
     assert [n.dof for n in c.nodes] == [n.dof for n in db.nodes] and [e.nlist for e in c.elems] == [e.nlist for e in db.elems]
     assert [[(n, v.M) for n, v in bc.nodal] for _, bc in c.bcs] == [[(n, v.M) for n, v in bc.nodal] for _, bc in db.bcs]
+
+
+def test_codec_fuzz_python_vs_native(host, tmp_path):
+    """Random databases (hypothesis): the Python codec is its own inverse and the independent C++ codec
+    re-serialises every one of them byte for byte — negative ids, empty and long lists, odd doubles,
+    non-ASCII names, results present or absent."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    i32 = st.integers(-2**31, 2**31 - 1)
+    f64 = st.floats(allow_nan=False, width=64)
+    text = st.text(max_size=12)
+    mat_st = st.builds(lambda r, c, fill: stdb.MatrixST([fill * (k + 1) for k in range(r * c)], r, c),
+                       st.integers(0, 4), st.integers(0, 4), f64)
+    node = st.builds(stdb.Node, id=i32, x=f64, y=f64, z=f64, elist=st.lists(i32, max_size=5), dof=st.lists(i32, max_size=3),
+                     dispx=st.lists(f64, max_size=3), dispy=st.lists(f64, max_size=3), dispz=st.lists(f64, max_size=3))
+    elem = st.builds(stdb.Element, id=i32, type=text, pid=i32, matid=i32, nlist=st.lists(i32, max_size=8),
+                     strain=st.lists(mat_st, max_size=2), stress=st.lists(mat_st, max_size=2))
+    mat = st.builds(stdb.Material, id=i32, type=text, name=text, E=f64, poisson=f64, colorid=i32)
+    bc = st.tuples(i32, st.builds(stdb.BoundaryCondition, type=text, name=text, id=i32, colorid=i32,
+                                  nodal=st.lists(st.tuples(i32, mat_st), max_size=4)))
+    ana = st.one_of(st.none(), st.builds(stdb.Analysis, type=text, linsolver=text, tolerance=f64, itermax=i32, incnumb=i32,
+                                         result_stepno=i32))
+    db_st = st.builds(stdb.Database, nodes=st.lists(node, max_size=4), elems=st.lists(elem, max_size=3),
+                      mats=st.lists(mat, max_size=2), bcs=st.lists(bc, max_size=2), ndof=i32, analysis=ana,
+                      info_raw=st.one_of(st.none(), st.binary(max_size=6)))
+    a, b = tmp_path / "f.STdb", tmp_path / "g.STdb"
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(db_st)
+    def run(db):
+        raw = stdb.encode(db)
+        assert stdb.encode(stdb.decode(raw)) == raw
+        a.write_bytes(raw)
+        r = subprocess.run([host, "--roundtrip", str(a), str(b)], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, r.stderr
+        assert b.read_bytes() == raw
+
+    run()
