@@ -69,6 +69,7 @@ __device__ void scalar_step(CgState *st, int step) {
         }
     } else if (step == SC_AFTER_UPDATE) {                // partial: [0] = r.r, [1] = r.z
         finish_iteration(st, st->partial[0], st->partial[1]);
+        if (st->done) st->x_pending = 1;                 // x += alpha p of this iteration rides in k_direction, which now skips
     } else if (step == SC_AFTER_REFRESH) {               // + [2] = 2 b.cx, [3] = (A cx).cx from the SpMV
         st->nmv++;
         const double v1 = st->partial[3] - st->partial[2];
@@ -616,16 +617,15 @@ k_cg_init(int64_t n, const double *__restrict__ b, const double *__restrict__ d2
     grid_reduce<2>(v, partials, counter, st, 0, SC_INIT, run_scalar);
 }
 
-// x += alpha p; r -= alpha mv; sums r.r and r.(r d^2)
+// r -= alpha mv; sums r.r and r.(r d^2).  The matching x += alpha p is applied by k_direction, which
+// reads p anyway (one vector less per iteration), or by k_x_tail when this iteration ends the solve.
 __global__ void __launch_bounds__(VEC_THREADS)
-k_update(int64_t n, double *__restrict__ x, double *__restrict__ r, const double *__restrict__ p,
-         const double *__restrict__ mv, const double *__restrict__ d2, double *partials, unsigned int *counter,
-         CgState *st, bool run_scalar) {
+k_update(int64_t n, double *__restrict__ r, const double *__restrict__ mv, const double *__restrict__ d2,
+         double *partials, unsigned int *counter, CgState *st, bool run_scalar) {
     if (st->done) return;
     const double alpha = st->alpha;
     double v[2] = {0.0, 0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        x[i] = x[i] + alpha * p[i];
         const double ri = r[i] - alpha * mv[i];
         r[i] = ri;
         v[0] += ri * ri;
@@ -662,14 +662,29 @@ k_refresh(int64_t n, const double *__restrict__ b, const double *__restrict__ mv
     grid_reduce<3>(v, partials, counter, st, 0, SC_AFTER_REFRESH, run_scalar);
 }
 
+// x += alpha p (ordinary iterations; a refresh iteration has already installed its candidate x), then
 // p = r d^2 + beta p
+template <bool WITH_X>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_direction(int64_t n, const double *__restrict__ r, const double *__restrict__ d2, double *__restrict__ p,
-            const CgState *st) {
+            double *__restrict__ x, const CgState *st) {
     if (st->done) return;
-    const double beta = st->beta;
+    const double beta = st->beta, alpha = st->alpha;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double pi = p[i];
+        if (WITH_X) x[i] = x[i] + alpha * pi;
+        p[i] = r[i] * d2[i] + beta * pi;
+    }
+}
+
+// the x += alpha p of the iteration that ended the solve (p and alpha are frozen once the state says done)
+__global__ void __launch_bounds__(VEC_THREADS)
+k_x_tail(int64_t n, double *__restrict__ x0, double *__restrict__ x1, const double *__restrict__ p, const CgState *st) {
+    if (!st->x_pending) return;
+    double *x = st->x_in_alt ? x1 : x0;
+    const double alpha = st->alpha;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = r[i] * d2[i] + beta * p[i];
+        x[i] = x[i] + alpha * p[i];
 }
 
 __global__ void k_scatter_full(int64_t nloc3, const double *__restrict__ x, double *__restrict__ ufull, int64_t dof0) {
@@ -915,8 +930,8 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
             const bool refresh = rupd > 0 && kk % rupd == 0;
             STAN_TRY(spmv(h->d_p.p, 0, SC_AFTER_SPMV));
             if (!refresh) {
-                k_update<<<gv, VEC_THREADS, 0, s>>>(n, x, h->d_r.p, h->d_p.p, h->d_mv.p, h->d_d2.p, h->d_partials.p,
-                                                    h->d_counter.p, st, single);
+                k_update<<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_mv.p, h->d_d2.p, h->d_partials.p, h->d_counter.p, st,
+                                                    single);
                 launches++;
                 STAN_TRY(reduce_tail(SC_AFTER_UPDATE));
             } else {
@@ -929,7 +944,8 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
                 STAN_TRY(reduce_tail(SC_AFTER_REFRESH));
                 double *t = x; x = xalt; xalt = t;         // accepted unless the state says type 7
             }
-            k_direction<<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, h->d_p.p, st);
+            if (refresh) k_direction<false><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, h->d_p.p, x, st);
+            else         k_direction<true><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, h->d_p.p, x, st);
             launches++;
         }
         return STAN_OK;
@@ -969,6 +985,10 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     }
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
+    if (hst->x_pending) {
+        k_x_tail<<<gv, VEC_THREADS, 0, s>>>(n, h->d_x.p, h->d_xalt.p, h->d_p.p, st);
+        launches++;
+    }
     STAN_CUDA(cudaEventRecord(h->ev1, s));
     STAN_CUDA(cudaStreamSynchronize(s));
     float ms = 0.f;
@@ -991,7 +1011,7 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     rep->solve_ms = ms;
     rep->spmv_ms = spmv_ms;
     rep->spmv_bytes = spmv_algorithmic_bytes(h);
-    rep->iter_bytes = rep->spmv_bytes + 88 * n;
+    rep->iter_bytes = rep->spmv_bytes + 80 * n;
     rep->kernel_launches = launches;
     h->launches += launches;
     if (p2p) {                                             // a peer never raised its flag (spin timed out)

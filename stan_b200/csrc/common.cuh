@@ -127,7 +127,7 @@ struct CgState {
     int32_t maxits, rupdate, merit_check, counter_off;
     int64_t restart;
     int32_t x_in_alt; // 1 when the accepted iterate lives in the alternate x buffer
-    int32_t pad;
+    int32_t x_pending;// 1 when the solve ended at an ordinary iteration whose x += alpha p is still owed
     CommDev *comm;    // peer-memory reductions (multi-GPU P2P mode), else nullptr
     unsigned long long red_seq;   // reductions published so far (same on every rank)
 };
