@@ -2,6 +2,7 @@
 
 #include <cstdlib>
 #include <fstream>
+#include <iterator>
 #include <unordered_set>
 
 namespace bdf {
@@ -13,8 +14,9 @@ bool starts_with(const std::string &s, const char *p) { return s.rfind(p, 0) == 
 // int.Parse / int.TryParse: optional surrounding blanks, optional sign, digits only
 bool parse_int(const std::string &s, int32_t &out) {
     size_t a = 0, b = s.size();
-    while (a < b && (s[a] == ' ' || s[a] == '\t')) a++;
-    while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\t')) b--;
+    auto ws = [](char c) { return c == ' ' || (c >= '\t' && c <= '\r'); };   // NumberStyles.AllowLeading/TrailingWhite
+    while (a < b && ws(s[a])) a++;
+    while (b > a && ws(s[b - 1])) b--;
     if (a == b) return false;
     size_t i = a;
     if (s[i] == '+' || s[i] == '-') i++;
@@ -31,11 +33,29 @@ bool parse_int(const std::string &s, int32_t &out) {
     return true;
 }
 
+// double.Parse(s, InvariantCulture) for what a deck can contain: [ws][sign]digits[.digits][e[sign]digits][ws]
+// (strtod alone would also take hex floats, "inf" and "nan", which .NET rejects in this spelling)
 bool parse_double(const std::string &s, double &out) {
-    if (s.empty()) return false;
-    char *end = nullptr;
-    out = strtod(s.c_str(), &end);
-    return end && *end == '\0' && end != s.c_str();
+    size_t a = 0, b = s.size();
+    auto ws = [](char c) { return c == ' ' || (c >= '\t' && c <= '\r'); };
+    while (a < b && ws(s[a])) a++;
+    while (b > a && ws(s[b - 1])) b--;
+    size_t i = a;
+    if (i < b && (s[i] == '+' || s[i] == '-')) i++;
+    size_t nd = 0;
+    while (i < b && s[i] >= '0' && s[i] <= '9') { i++; nd++; }
+    if (i < b && s[i] == '.') { i++; while (i < b && s[i] >= '0' && s[i] <= '9') { i++; nd++; } }
+    if (nd == 0) return false;
+    if (i < b && (s[i] == 'e' || s[i] == 'E')) {
+        i++;
+        if (i < b && (s[i] == '+' || s[i] == '-')) i++;
+        size_t ne = 0;
+        while (i < b && s[i] >= '0' && s[i] <= '9') { i++; ne++; }
+        if (ne == 0) return false;
+    }
+    if (i != b) return false;
+    out = strtod(s.substr(a, b - a).c_str(), nullptr);
+    return true;
 }
 
 void replace_all(std::string &s, const std::string &from, const std::string &to) {
@@ -100,12 +120,15 @@ bool parse_element(const std::string &input, stdb::Element &e) {
 }  // namespace
 
 bool read_nastran_mesh(const std::string &path, stdb::Database &db, ImportReport &rep, std::string &err) {
-    std::ifstream in(path);
+    std::ifstream in(path, std::ios::binary);
     if (!in) { err = "cannot open " + path; return false; }
-    std::vector<std::string> data;
-    for (std::string line; std::getline(in, line);) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        data.push_back(line);
+    const std::string all((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    std::vector<std::string> data;                               // File.ReadAllLines: \r\n, \n and lone \r end a line
+    for (size_t a = 0; a < all.size();) {
+        size_t b = a;
+        while (b < all.size() && all[b] != '\n' && all[b] != '\r') b++;
+        data.push_back(all.substr(a, b - a));
+        a = b + ((b + 1 < all.size() && all[b] == '\r' && all[b + 1] == '\n') ? 2 : 1);
     }
     std::unordered_set<int32_t> node_ids, elem_ids;
     for (size_t i = 0; i < data.size(); i++) {

@@ -2,7 +2,7 @@
 // every part contributes its own point list — the distinct node IDs of its elements in ascending
 // order (Part.DetectPartNodes, Part.cs:721-747), moved by the displacement of the increment
 // (Part.UpdateNode, :581-594) — and its hexahedra (VTK cell type 12, :869-886); parts are appended one
-// after the other without merging points (vtkAppendFilter), so interface nodes appear once per part.
+// after the other in ascending PID order (PartLib) without merging points (vtkAppendFilter), so interface nodes appear once per part.
 // Point data = the selected nodal-averaged arrays, named without the " INC n" suffix (:920-934), in
 // the order Displacement, Strain, Stress (ExportWindow.xaml.cs:66-68).
 #include "vtu.hpp"
@@ -71,20 +71,20 @@ bool write_increment(const stdb::Database &db, const std::vector<double> &disp, 
     pos.reserve(nn * 2);
     for (size_t i = 0; i < nn; i++) pos[db.nodes[i].id] = i;
 
-    std::vector<int32_t> part_order;                      // parts in order of first appearance in ElemLib
+    // PartLib = distinct PIDs of ElemLib, sorted (Database.cs:98-108): std::map iterates in that order
     std::map<int32_t, std::vector<int32_t>> part_nodes;
     for (const auto &e : db.elems) {
         if (e.type.find("HEX") == std::string::npos) continue;
-        auto it = part_nodes.find(e.pid);
-        if (it == part_nodes.end()) { part_order.push_back(e.pid); it = part_nodes.emplace(e.pid, std::vector<int32_t>()).first; }
-        it->second.insert(it->second.end(), e.nlist.begin(), e.nlist.end());
+        auto &ids = part_nodes[e.pid];
+        ids.insert(ids.end(), e.nlist.begin(), e.nlist.end());
     }
     std::vector<float> xyz;
     std::vector<size_t> src;                              // node position behind every output point
     std::vector<int64_t> conn, offsets;
     std::vector<uint8_t> types;
-    for (int32_t pid : part_order) {
-        auto &ids = part_nodes[pid];
+    for (auto &part : part_nodes) {
+        const int32_t pid = part.first;
+        auto &ids = part.second;
         std::sort(ids.begin(), ids.end());
         ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
         const int64_t base = (int64_t)src.size();

@@ -209,3 +209,46 @@ def test_codec_fuzz_python_vs_native(host, tmp_path):
         assert b.read_bytes() == raw
 
     run()
+
+
+def test_bdf_import_fuzz_against_second_restatement(host, tmp_path):
+    """Generated decks with the oddities real decks have (exponent-less floats, blank fields, continuation
+    lines, '+' markers, comments, CRLF, duplicates, junk): the native importer and the independent Python
+    restatement of the reference's parser (oracle/bdf_import.py) must agree on every node, element and
+    on the number of import errors."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    from oracle import bdf_import
+
+    num = st.sampled_from(["1.5", "-2.5", ".5", "-.25", "1.-3", "-1.5-3", "7.11-15", "7.11+15", "1e-3", "2.E+2", "0.0", "12.",
+                           "", "abc", "1.2.3", "-", "1-", "3", "-7", "1e", "+4.5", "1,5"])
+    ident = st.one_of(st.integers(1, 40).map(str), st.sampled_from(["", "x1", "-3", "99999999", "123456789", "1.0", "+7"]))
+    field = lambda s: s.map(lambda v: v[:8].rjust(8))                       # noqa: E731
+    grid = st.tuples(field(ident), field(st.sampled_from(["", "", "", "0"])), field(num), field(num), field(num),
+                     st.sampled_from(["", "       0", "  ", "\t"])).map(lambda t: "GRID    " + "".join(t))
+    nid = st.one_of(st.integers(1, 60).map(str), st.sampled_from(["", "q", "+", "1+", "2147483648"]))
+    chexa = st.tuples(st.sampled_from(["CHEXA   ", "CHEXA  ", " CHEXA   ", "$CHEXA  ", "XCHEXA  "]), field(ident), field(ident),
+                      st.lists(field(nid), min_size=0, max_size=6), st.sampled_from(["+", "+E1", "", " "]),
+                      st.sampled_from(["+       ", "+E1     ", "        ", "*       ", ""]), st.lists(field(nid), min_size=0, max_size=3)) \
+        .map(lambda t: t[0] + t[1] + t[2] + "".join(t[3]) + t[4] + "\n" + t[5] + "".join(t[6]))
+    other = st.sampled_from(["$$ comment", "", "ENDDATA", "CTETRA         9       1       1       2       3       4", "GRIDX  1",
+                             "BEGIN BULK", " GRID          1             0.0     0.0     0.0", "+ stray continuation"])
+    deck = st.tuples(st.lists(st.one_of(grid, chexa, other), min_size=0, max_size=14), st.sampled_from(["\n", "\r\n"]),
+                     st.booleans()).map(lambda t: t[1].join(l.replace("\n", t[1]) for l in t[0]) + (t[1] if t[2] else ""))
+    bdf, out = tmp_path / "f.bdf", tmp_path / "f.STdb"
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(deck)
+    def run(text):
+        bdf.write_bytes(text.encode())
+        r = subprocess.run([host, "--import-bdf", str(bdf), str(out)], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, r.stderr
+        rep = json.loads(r.stdout)
+        nodes, elems, errors = bdf_import.read_nastran_mesh(text)
+        db = stdb.decode(out.read_bytes())
+        assert [(n.id, n.x, n.y, n.z) for n in db.nodes] == [(k, *v) for k, v in nodes.items()]
+        assert [(e.id, e.pid, e.nlist, e.type) for e in db.elems] == [(k, v[0], v[1], v[2]) for k, v in elems.items()]
+        assert rep["import_errors"] == errors and rep["nodes"] == len(nodes) and rep["elements"] == len(elems)
+
+    run()
