@@ -93,3 +93,39 @@ def read_nastran_mesh(text: str):
                     errors += 1
         i += 1
     return nodes, elems, errors
+
+
+def parse_bc_text(text: str):
+    """BOX_BC.Paste_Click (/root/reference/src/STAN_PrePost/BOX_BC.xaml.cs:228-270): rows "NID x y z" split by
+    ',' then ' ' then TAB (first split that yields exactly four fields), unparsable rows skipped, nothing read
+    from a text of fewer than two lines."""
+    rows = []
+    lines = text.split("\n")
+    if len(lines) <= 1:
+        return rows
+    for s in lines:
+        f = s.split(",")
+        if len(f) != 4:
+            f = s.split(" ")
+            if len(f) != 4:
+                f = s.split("\t")
+        if len(f) != 4:
+            continue
+        try:
+            rows.append((_int_parse(f[0]), _double_parse(f[1]), _double_parse(f[2]), _double_parse(f[3])))
+        except (ValueError, OverflowError):
+            pass
+    return rows
+
+
+def apply_bc(rows, known_ids):
+    """BoundaryCondition.Add (BoundaryCondition.cs:87-98): unknown nodes dropped, a repeated node raises."""
+    out, seen = [], set()
+    for nid, x, y, z in rows:
+        if nid not in known_ids:
+            continue
+        if nid in seen:
+            raise KeyError(nid)
+        seen.add(nid)
+        out.append((nid, [x, y, z]))
+    return out

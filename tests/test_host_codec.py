@@ -252,3 +252,37 @@ def test_bdf_import_fuzz_against_second_restatement(host, tmp_path):
         assert rep["import_errors"] == errors and rep["nodes"] == len(nodes) and rep["elements"] == len(elems)
 
     run()
+
+
+def test_bc_paste_fuzz_against_second_restatement(host, tmp_path):
+    """Pasted boundary-condition text: native `--build` against oracle/bdf_import.parse_bc_text / apply_bc."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    from oracle import bdf_import
+
+    m = mesh.beam(1, 1, 2)                                                   # nodes 1..12
+    bdf, out, txt = tmp_path / "m.bdf", tmp_path / "m.STdb", tmp_path / "bc.txt"
+    mesh.write_bdf(m, str(bdf))
+    tok = st.sampled_from(["1", "2", "3", "7", "12", "13", "0", "-1", "1.0", "1e0", "0.5", "-2.5e-3", "+4", ".5", "5.", "", "x",
+                           "1 ", " 1", "1\r", "99999999999", "1e", "--1"])
+    sep = st.sampled_from([",", " ", "\t", "\t", "\t"])
+    row = st.tuples(st.lists(tok, min_size=2, max_size=5), sep).map(lambda t: t[1].join(t[0]))
+    text = st.tuples(st.lists(row, min_size=0, max_size=8), st.sampled_from(["\n", "\r\n"]), st.booleans()) \
+        .map(lambda t: t[1].join(t[0]) + (t[1] if t[2] else ""))
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+    @given(text)
+    def run(s):
+        txt.write_bytes(s.encode())
+        r = subprocess.run([host, "--build", str(bdf), str(out), "--spc", str(txt)], capture_output=True, text=True, timeout=60)
+        try:
+            want = bdf_import.apply_bc(bdf_import.parse_bc_text(s), set(range(1, m.n_nodes + 1)))
+        except KeyError:
+            assert r.returncode == 3 and "listed twice" in r.stderr
+            return
+        assert r.returncode == 0, r.stderr
+        (_, bc), = stdb.decode(out.read_bytes()).bcs
+        assert [(n, v.M) for n, v in bc.nodal] == want
+
+    run()
