@@ -148,6 +148,22 @@ class UpperCsr:
         self.nnz = lib().stan_oracle_csr_nnz(handle)
         self._arrays = None
 
+    @classmethod
+    def from_dense_upper(cls, A):
+        """Upper triangle (nonzeros, diagonal always) of a small dense symmetric matrix — hand-worked test cases."""
+        A = np.asarray(A, dtype=np.float64)
+        n = A.shape[0]
+        rp, col, val = [0], [], []
+        for i in range(n):
+            for j in range(i, n):
+                if j == i or A[i, j] != 0.0:
+                    col.append(j); val.append(A[i, j])
+            rp.append(len(col))
+        rp, col, val = np.array(rp, np.int64), np.array(col, np.int32), np.array(val)
+        fn = lib().stan_oracle_csr_from_arrays
+        fn.restype = C.c_void_p
+        return cls(fn(C.c_int64(n), _p(rp), _p(col), _p(val)), 0)
+
     def arrays(self):
         if self._arrays is None:
             rp = np.zeros(self.n + 1, dtype=np.int64)

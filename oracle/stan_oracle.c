@@ -340,6 +340,20 @@ OX void stan_oracle_csr_free(oracle_csr *m) {
     if (!m) return;
     free(m->rowptr); free(m->col); free(m->val); free(m);
 }
+/* An upper-triangle CRS built from caller arrays: lets the tests feed hand-worked matrices to the
+ * ALGLIB restatements (lincg, skyline Cholesky) without going through the mesh assembly. */
+OX oracle_csr *stan_oracle_csr_from_arrays(int64_t n, const int64_t *rowptr, const int32_t *col, const double *val) {
+    oracle_csr *m = calloc(1, sizeof *m);
+    m->n = n;
+    m->nnz = rowptr[n];
+    m->rowptr = malloc((size_t)(n + 1) * sizeof(int64_t));
+    m->col = malloc((size_t)(m->nnz + 1) * sizeof(int32_t));
+    m->val = malloc((size_t)(m->nnz + 1) * sizeof(double));
+    memcpy(m->rowptr, rowptr, (size_t)(n + 1) * sizeof(int64_t));
+    memcpy(m->col, col, (size_t)m->nnz * sizeof(int32_t));
+    memcpy(m->val, val, (size_t)m->nnz * sizeof(double));
+    return m;
+}
 OX int64_t stan_oracle_csr_n(const oracle_csr *m) { return m->n; }
 OX int64_t stan_oracle_csr_nnz(const oracle_csr *m) { return m->nnz; }
 OX void stan_oracle_csr_copy(const oracle_csr *m, int64_t *rowptr, int32_t *col, double *val) {

@@ -273,3 +273,25 @@ def test_mesh_generator_and_bdf(tmp_path):
     lines = p.read_text().splitlines()
     assert sum(l.startswith("GRID") for l in lines) == r.n_nodes
     assert sum(l.startswith("CHEXA") for l in lines) == r.n_elem
+
+
+def test_alglib_restatements_on_hand_worked_matrices(oracle):
+    """Hand-worked known answers for the two ALGLIB restatements, no mesh involved.
+    A = [[4,2,0,0],[2,5,3,0],[0,3,10,1],[0,0,1,2]]: U^T U by hand is u11 = 2, u12 = 1, u22 = sqrt(5-1) = 2,
+    u23 = 3/2, u33 = sqrt(10 - 9/4), u34 = 1/u33, u44 = sqrt(2 - 1/7.75); skyline envelope 1+2+2+2 = 7.
+    CG on a 2x2 SPD system reaches the exact solution in two iterations (Jacobi-preconditioned or not)."""
+    A = np.array([[4.0, 2, 0, 0], [2, 5, 3, 0], [0, 3, 10, 1], [0, 0, 1, 2]])
+    x_true = np.array([1.0, -1.0, 2.0, 0.5])
+    K = oracle.UpperCsr.from_dense_upper(A)
+    x, tt, env = oracle.cholesky_skyline(K, A @ x_true)
+    assert tt == 1 and env == 7
+    np.testing.assert_allclose(x, x_true, rtol=0, atol=4e-16 * 8)
+    np.testing.assert_allclose(oracle.sym_spmv(K, x_true), A @ x_true, rtol=0, atol=1e-15)
+    # indefinite: the second pivot 1 - 4 < 0 -> -3 and zeros
+    xi, tt, _ = oracle.cholesky_skyline(oracle.UpperCsr.from_dense_upper([[1.0, 2.0], [2.0, 1.0]]), np.array([1.0, 1.0]))
+    assert tt == -3 and not xi.any()
+    B = np.array([[4.0, 1.0], [1.0, 3.0]])
+    b = np.array([1.0, 2.0])
+    xc, rep = oracle.lincg(oracle.UpperCsr.from_dense_upper(B), b, oracle.cg_opts(epsf=1e-14, maxits=10, merit_check=0))
+    np.testing.assert_allclose(xc, [1.0 / 11.0, 7.0 / 11.0], rtol=1e-14)
+    assert rep.iterationscount == 2 and rep.terminationtype == 1 and rep.nmv == 3
