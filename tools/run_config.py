@@ -18,8 +18,9 @@ with Solver() as s:
     t0 = time.perf_counter()
     s.SetModel(m)
     ni = s.AssignDOF()
+    s.ParallelAssembly_K()                # the first call pays pool growth and lazy module loading
     a = s.ParallelAssembly_K()
-    cg = s.LinearSolver_CG(merit_check=0, IterMax=maxits)
+    cg =s.LinearSolver_CG(merit_check=0, IterMax=maxits)
     rc = s.Recovery_Stress()
     U = s.Include_BC_DOF()
     wall = time.perf_counter() - t0
