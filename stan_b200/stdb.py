@@ -388,3 +388,33 @@ def results(db: Database):
     strain = np.array([e.strain[1].array() for e in db.elems])
     stress = np.array([e.stress[1].array() for e in db.elems])
     return ni, disp, strain, stress
+
+
+def to_model(db: Database) -> Model:
+    """The flat model Solver.SolverLinearStatics reads from a database (Solver.cs:71-152): positions in
+    NodeLib / ElemLib / MatLib order replace IDs, SPC and PointLoad entries are concatenated in BCLib order.
+    Raises on what the native path does not cover (non-hex8 elements, unknown node or material IDs)."""
+    node_pos = {n.id: i for i, n in enumerate(db.nodes)}
+    mat_pos = {m.id: i for i, m in enumerate(db.mats)}
+    types = {"HEX8_G2": HEX8_G2, "HEX8_G1": HEX8_G1}
+    try:
+        conn = np.array([[node_pos[v] for v in e.nlist] for e in db.elems], dtype=np.int32).reshape(-1, 8)
+        etype = np.array([types[e.type] for e in db.elems], dtype=np.uint8)
+        emat = np.array([mat_pos[e.matid] for e in db.elems], dtype=np.int32)
+    except KeyError as k:
+        raise ValueError(f"database entry {k} is outside the linear-static hex8 path") from None
+    spc_n, spc_v, load_n, load_v = [], [], [], []
+    for _, bc in db.bcs:
+        dst_n, dst_v = (spc_n, spc_v) if bc.type == "SPC" else (load_n, load_v) if bc.type == "PointLoad" else (None, None)
+        if dst_n is None:
+            continue
+        for nid, mat in bc.nodal:
+            dst_n.append(node_pos[nid])
+            dst_v.append((list(mat.M) + [0.0, 0.0, 0.0])[:3])
+    a = db.analysis or Analysis()
+    return Model(xyz=np.array([[n.x, n.y, n.z] for n in db.nodes], dtype=np.float64).reshape(-1, 3), conn=conn, elem_type=etype,
+                 elem_mat=emat, elem_pid=np.array([e.pid for e in db.elems], dtype=np.int32),
+                 mat_E=np.array([m.E for m in db.mats]), mat_nu=np.array([m.poisson for m in db.mats]),
+                 spc_node=np.array(spc_n, dtype=np.int32), spc_val=np.array(spc_v, dtype=np.float64).reshape(-1, 3),
+                 load_node=np.array(load_n, dtype=np.int32), load_val=np.array(load_v, dtype=np.float64).reshape(-1, 3),
+                 tolerance=a.tolerance, max_iter=a.itermax, lin_solver=a.linsolver)

@@ -286,3 +286,17 @@ def test_bc_paste_fuzz_against_second_restatement(host, tmp_path):
         assert [(n, v.M) for n, v in bc.nodal] == want
 
     run()
+
+
+def test_to_model_inverts_from_model():
+    m = mesh.beam(3, 2, 4, jitter=True, n_parts=2, tolerance=3e-7, max_iter=77, elem_type=mesh.HEX8_G1)
+    m.lin_solver = "Cholesky"
+    back = stdb.to_model(stdb.decode(stdb.encode(stdb.from_model(m))))
+    for f in ("xyz", "conn", "elem_type", "elem_mat", "elem_pid", "mat_E", "mat_nu", "spc_node", "spc_val", "load_node", "load_val"):
+        a, b = getattr(m, f), getattr(back, f)
+        assert a.dtype == b.dtype and np.array_equal(a, b), f
+    assert (back.tolerance, back.max_iter, back.lin_solver) == (3e-7, 77, "Cholesky")
+    db = stdb.from_model(m)
+    db.elems[0].type = "TET4_G2"
+    with pytest.raises(ValueError):
+        stdb.to_model(db)
