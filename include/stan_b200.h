@@ -32,15 +32,13 @@ extern "C" {
 #define STAN_E_CUDA       -2  /* CUDA runtime failure (message has the detail) */
 #define STAN_E_SINGULAR   -3  /* Jacobian determinant == 0 (MatrixST.cs:298,317 throws) */
 #define STAN_E_STATE      -4  /* call order violated (e.g. solve before assemble) */
-#define STAN_E_CAPACITY   -5  /* a node couples to more nodes than STAN_MAX_ROW_BLOCKS */
+/* -5 was STAN_E_CAPACITY (row wider than 96 blocks) in round 1: rows of any width are accepted now */
 #define STAN_E_DOFMAP     -6  /* AssignDOF failed: no start node / disconnected mesh (Database.cs:178-196, :218) */
 #define STAN_E_COMM       -7  /* NCCL / multi-GPU failure */
-#define STAN_E_NOMEM      -8  /* the direct solver's skyline does not fit the device */
+#define STAN_E_NOMEM      -8  /* device memory: the direct solver's skyline (or an assembly work area) does not fit */
 
 #define STAN_HEX8_G1 1        /* Element.Type "HEX8_G1", FE_Library.cs:63-89 */
 #define STAN_HEX8_G2 2        /* Element.Type "HEX8_G2", FE_Library.cs:91-131 */
-
-#define STAN_MAX_ROW_BLOCKS 96
 
 typedef struct stan_handle stan_handle;
 
@@ -84,9 +82,11 @@ typedef struct {
     int64_t n_fixed;           /* |Distinct(Fix_DOF)| (Solver.cs:117) */
     int64_t n_rows_local;      /* block rows (nodes) owned by this rank */
     int64_t n_blocks_local;    /* stored 3x3 blocks on this rank */
-    int64_t nnz_upper;         /* entries of the reference's upper-triangle CRS (global) */
+    int64_t nnz_upper;         /* entries of the reference's upper-triangle CRS; counted lazily: 0 until a
+                                  stan_get_csr_upper_size call on this model, its result afterwards */
     int64_t assembly_bytes;    /* algorithmic bytes of the assembly kernel */
-    double  assembly_flops;    /* algorithmic flops of the element integration */
+    double  assembly_flops;    /* algorithmic flops of the element integration: 17.3 k per HEX8_G2
+                                  element + 2.2 k per HEX8_G1 element */
     double  pattern_ms;        /* incidence + block pattern build */
     double  assembly_ms;       /* hex8 integration + deterministic row assembly kernel */
     double  total_ms;          /* whole stan_assemble call on the device */
@@ -175,6 +175,13 @@ int stan_get_csr_upper(stan_handle *h, int64_t *rowptr, int32_t *col, double *va
 int stan_element_stiffness(stan_handle *h, int64_t first, int64_t count, double *ke);
 /* y = K x on the stored matrix, x and y in full DOF space (fixed DOFs act as identity rows). */
 int stan_spmv(stan_handle *h, const double *x_full, double *y_full);
+/* Trajectory of the CG recurrences, for pinning R5 iteration by iteration against the CPU restatement of
+ * alglib.lincgiteration (SolverFunctions.cs:304): with capacity > 0 the next stan_solve_cg records, for
+ * k = 1 .. min(capacity, iterationscount), the row { ||r_k||^2, alpha_k, beta_k (0 on a restart and at the
+ * final iteration), energy functional x'Ax - 2b'x on true-residual refresh iterations else NaN }.
+ * stan_get_cg_history returns the number of rows and copies count x 4 doubles (hist4 may be NULL). */
+int stan_set_cg_history(stan_handle *h, int32_t capacity);
+int stan_get_cg_history(stan_handle *h, int32_t *count, double *hist4);
 /* Device time of `reps` back-to-back SpMV launches on the assembled matrix (CUDA events). */
 int stan_time_spmv(stan_handle *h, int32_t reps, double *ms_per_launch, int64_t *bytes_per_launch);
 

@@ -28,7 +28,7 @@ def build(force: bool = False) -> str:
 class CgOpts(C.Structure):
     _fields_ = [("epsf", C.c_double), ("maxits", C.c_int32), ("its_before_rupdate", C.c_int32),
                 ("its_before_restart", C.c_int32), ("merit_check", C.c_int32),
-                ("zero_based_counter", C.c_int32), ("parallel_spmv", C.c_int32)]
+                ("zero_based_counter", C.c_int32), ("parallel_spmv", C.c_int32), ("dot_mode", C.c_int32)]
 
 
 class CgReport(C.Structure):
@@ -43,9 +43,9 @@ class PathStats(C.Structure):
 
 
 def cg_opts(epsf=1e-8, maxits=0, its_before_rupdate=10, its_before_restart=0, merit_check=1,
-            zero_based_counter=0, parallel_spmv=0) -> CgOpts:
+            zero_based_counter=0, parallel_spmv=0, dot_mode=0) -> CgOpts:
     return CgOpts(epsf, maxits, its_before_rupdate, its_before_restart, merit_check, zero_based_counter,
-                  parallel_spmv)
+                  parallel_spmv, dot_mode)
 
 
 def lib():
@@ -207,6 +207,19 @@ def lincg(K: UpperCsr, b, opts: CgOpts):
     return x, rep
 
 
+def lincg_history(K: UpperCsr, b, opts: CgOpts, cap: int):
+    """lincg plus its per-iteration trajectory: rows k = 1.. of (||r_k||^2, alpha_k, beta_k, energy functional
+    on refresh iterations else NaN) — the same record stan_get_cg_history returns."""
+    if not opts.merit_check and opts.maxits <= 0:
+        raise ValueError("merit_check=0 needs maxits > 0")
+    b = _f64(b)
+    x = np.zeros(K.n)
+    rep = CgReport()
+    hist = np.full((cap, 4), np.nan)
+    lib().stan_oracle_lincg_hist(C.c_void_p(K._h), _p(b), C.byref(opts), _p(x), C.byref(rep), _p(hist), C.c_int64(cap))
+    return x, rep, hist[: min(cap, rep.iterationscount)]
+
+
 def cholesky_skyline(K: UpperCsr, b):
     """LinearSolver_Cholesky (SolverFunctions.cs:332-444): returns (x, terminationtype, envelope size)."""
     b = _f64(b)
@@ -269,3 +282,12 @@ def linear_statics(model, opts: CgOpts | None = None) -> PathResult:
 
 def threads() -> int:
     return int(lib().stan_oracle_threads())
+
+
+def set_threads(n: int | None = None) -> int:
+    """OpenMP team size of the oracle; default = the cores this process may run on (torchrun exports
+    OMP_NUM_THREADS=1 to its workers, which would silently turn the CPU baseline single-threaded)."""
+    if n is None:
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().stan_oracle_set_threads(int(n))
+    return threads()

@@ -546,6 +546,9 @@ typedef struct {
                                   1: tests use k-1 (counter incremented at loop end) */
     int32_t parallel_spmv;     /* 0: serial symmetric product in ALGLIB's sparsesmv order;
                                   1: expanded full CSR, OpenMP row-parallel (CPU baseline timing) */
+    int32_t dot_mode;          /* 0: plain left-to-right sums (ALGLIB); 1: blocked sums (1024-term partials added
+                                  in order) — a second, equally valid rounding of the same recurrences, used to
+                                  measure how far summation order alone moves the trajectory */
 } oracle_cg_opts;
 
 /* y = (U + U^T - diag) x from the upper CRS, in the accumulation order of ALGLIB's sparsesmv
@@ -604,15 +607,32 @@ static void full_spmv(const full_csr *F, const double *x, double *y) {
     }
 }
 
+static int g_dot_mode = 0;   /* set per solve from oracle_cg_opts.dot_mode (solves are not concurrent) */
+
 static double dot_seq(const double *a, const double *b, int64_t n) {
     double s = 0.0;
-    for (int64_t i = 0; i < n; i++) s += a[i] * b[i];
+    if (!g_dot_mode) {
+        for (int64_t i = 0; i < n; i++) s += a[i] * b[i];
+        return s;
+    }
+    for (int64_t i0 = 0; i0 < n; i0 += 1024) {
+        int64_t i1 = i0 + 1024 < n ? i0 + 1024 : n;
+        double t = 0.0;
+        for (int64_t i = i0; i < i1; i++) t += a[i] * b[i];
+        s += t;
+    }
     return s;
 }
 
-OX int stan_oracle_lincg(const oracle_csr *A, const double *b, const oracle_cg_opts *o, double *x,
-                         oracle_cg_report *rep) {
+/* One row of `hist` per completed iteration k = 1, 2, ...: { ||r_k||^2, alpha_k, beta_k (0 on a restart or
+ * when the solve ended at k), energy functional x'Ax - 2b'x on refresh iterations else NaN }.
+ * The same four numbers are exported by libstan_b200's stan_get_cg_history; the trajectory test compares them. */
+OX int stan_oracle_lincg_hist(const oracle_csr *A, const double *b, const oracle_cg_opts *o, double *x,
+                              oracle_cg_report *rep, double *hist, int64_t hist_cap) {
     int64_t n = A->n;
+    g_dot_mode = o->dot_mode;
+#define HIST(K, R2, AL, BE, ME) do { if (hist && (K) >= 1 && (K) <= hist_cap) { double *h_ = hist + 4 * ((K) - 1); \
+        h_[0] = (R2); h_[1] = (AL); h_[2] = (BE); h_[3] = (ME); } } while (0)
     double epsf = o->epsf;
     int maxits = o->maxits;
     if (epsf == 0.0 && maxits == 0) epsf = 1.0e-6;          /* lincgsetcond note, SolverFunctions.cs:292-293 */
@@ -664,6 +684,7 @@ OX int stan_oracle_lincg(const oracle_csr *A, const double *b, const oracle_cg_o
         if (!isfinite(alpha)) { rep->terminationtype = -4; goto done; }
         for (int64_t i = 0; i < n; i++) cx[i] = x[i] + alpha * p[i];
         int kk = k - off;
+        double merit_k = NAN;
         if (rupd == 0 || kk % rupd != 0) {
             for (int64_t i = 0; i < n; i++) cr[i] = r[i] - alpha * mv[i];
         } else {
@@ -672,14 +693,17 @@ OX int stan_oracle_lincg(const oracle_csr *A, const double *b, const oracle_cg_o
             double v1 = 0.0, v2 = 0.0;
             for (int64_t i = 0; i < n; i++) { v1 += mv[i] * cx[i]; v2 += 2 * b[i] * cx[i]; }
             v1 = v1 - v2;
+            merit_k = v1;
             if (o->merit_check && !(v1 < merit)) {         /* rounding stagnation: keep previous x */
                 rep->terminationtype = 7;
                 rep->iterationscount = k;
+                HIST(k, rep->r2, alpha, 0.0, v1);
                 goto done;
             }
             merit = v1;
         }
         double cr2 = dot_seq(cr, cr, n);
+        HIST(k, cr2, alpha, 0.0, merit_k);
         for (int64_t i = 0; i < n; i++) x[i] = cx[i];
         rep->iterationscount = k;
         rep->r2 = cr2;
@@ -688,10 +712,19 @@ OX int stan_oracle_lincg(const oracle_csr *A, const double *b, const oracle_cg_o
         /* z_new = M^-1 r_new; beta = (r_new . z_new) / (r . z) */
         double beta_num = 0.0;
         if (kk % restart != 0) {
-            for (int64_t i = 0; i < n; i++) { double czi = cr[i] * d2[i]; beta_num += czi * cr[i]; }
+            if (!g_dot_mode) {
+                for (int64_t i = 0; i < n; i++) { double czi = cr[i] * d2[i]; beta_num += czi * cr[i]; }
+            } else {
+                for (int64_t i0 = 0; i0 < n; i0 += 1024) {
+                    double t = 0.0;
+                    for (int64_t i = i0; i < n && i < i0 + 1024; i++) { double czi = cr[i] * d2[i]; t += czi * cr[i]; }
+                    beta_num += t;
+                }
+            }
             double uvar = rz;
             if (!isfinite(uvar) || uvar == 0.0 || !isfinite(beta_num)) { rep->terminationtype = -4; goto done; }
             double beta = beta_num / uvar;
+            HIST(k, cr2, alpha, beta, merit_k);
             for (int64_t i = 0; i < n; i++) { double czi = cr[i] * d2[i]; p[i] = czi + beta * p[i]; z[i] = czi; r[i] = cr[i]; }
         } else {
             for (int64_t i = 0; i < n; i++) { double czi = cr[i] * d2[i]; p[i] = czi; z[i] = czi; r[i] = cr[i]; }
@@ -700,8 +733,15 @@ OX int stan_oracle_lincg(const oracle_csr *A, const double *b, const oracle_cg_o
 done:
     if (F) { free(F->rowptr); free(F->col); free(F->val); free(F); }
     free(d2); free(r); free(z); free(p); free(mv); free(cx); free(cr);
+    g_dot_mode = 0;
     return rc;
 #undef SPMV
+#undef HIST
+}
+
+OX int stan_oracle_lincg(const oracle_csr *A, const double *b, const oracle_cg_opts *o, double *x,
+                         oracle_cg_report *rep) {
+    return stan_oracle_lincg_hist(A, b, o, x, rep, NULL, 0);
 }
 
 /* symmetric product exposed for tests */
@@ -869,6 +909,15 @@ OX int stan_oracle_threads(void) {
     return omp_get_max_threads();
 #else
     return 1;
+#endif
+}
+
+/* torchrun exports OMP_NUM_THREADS=1 to every worker; the CPU baseline legs set the team size explicitly. */
+OX void stan_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
 #endif
 }
 

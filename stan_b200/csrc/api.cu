@@ -107,15 +107,26 @@ int stan_create(const stan_options *opts, stan_handle **out) {
         return STAN_E_ARG;
     }
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    STAN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    STAN_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
-    STAN_CUDA(cudaEventCreate(&h->ev0)); STAN_CUDA(cudaEventCreate(&h->ev1));
-    STAN_CUDA(cudaEventCreate(&h->ev2)); STAN_CUDA(cudaEventCreate(&h->ev3));
-    cudaMemPool_t pool;
-    STAN_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-    uint64_t keep = UINT64_MAX;     // keep freed blocks cached: assemble/solve cycles reuse them
-    STAN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    STAN_TRY(upload_fe_tables());
+    auto init = [&]() -> int {
+        STAN_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        STAN_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+        STAN_CUDA(cudaEventCreate(&h->ev0)); STAN_CUDA(cudaEventCreate(&h->ev1));
+        STAN_CUDA(cudaEventCreate(&h->ev2)); STAN_CUDA(cudaEventCreate(&h->ev3));
+        cudaMemPool_t pool;
+        STAN_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        uint64_t keep = UINT64_MAX;     // keep freed blocks cached: assemble/solve cycles reuse them
+        STAN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        STAN_TRY(upload_fe_tables());
+        return STAN_OK;
+    };
+    const int rc = init();
+    if (rc != STAN_OK) {                 // release whatever was created; the error message stays
+        if (h->stream) cudaStreamDestroy(h->stream);
+        if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+        for (cudaEvent_t e : {h->ev0, h->ev1, h->ev2, h->ev3}) if (e) cudaEventDestroy(e);
+        delete h;
+        return rc;
+    }
     *out = h;
     return STAN_OK;
 }
@@ -133,7 +144,7 @@ int stan_destroy(stan_handle *h) {
     h->d_b.release(s); h->d_d2.release(s); h->d_err.release(s); h->d_x.release(s); h->d_xalt.release(s);
     h->d_r.release(s); h->d_p.release(s); h->d_mv.release(s); h->d_partials.release(s); h->d_state.release(s);
     h->d_counter.release(s); h->d_ufull.release(s); h->d_strain.release(s); h->d_stress.release(s);
-    h->d_cell.release(s); h->d_point.release(s); h->d_ke.release(s);
+    h->d_cell.release(s); h->d_point.release(s); h->d_ke.release(s); h->d_hist.release(s);
     for (auto &sl : h->scratch) if (sl.p) cudaFreeAsync(sl.p, s);
     if (h->h_state) cudaFreeHost(h->h_state);
     for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);
@@ -158,13 +169,23 @@ int stan_set_mesh(stan_handle *h, int64_t n_nodes, const double *xyz, int64_t n_
             set_error("element %lld references node %d outside [0,%lld)", (long long)(i / 8), conn[i], (long long)n_nodes);
             return STAN_E_ARG;
         }
-    for (int64_t e = 0; e < n_elem; e++)
+    int64_t n_g2 = 0;
+    for (int64_t e = 0; e < n_elem; e++) {
         if (elem_type[e] != STAN_HEX8_G1 && elem_type[e] != STAN_HEX8_G2) {
             set_error("element %lld has unsupported type %d (only HEX8_G1/HEX8_G2)", (long long)e, (int)elem_type[e]);
             return STAN_E_ARG;
         }
+        n_g2 += elem_type[e] == STAN_HEX8_G2;
+    }
+    int32_t mmax = 0;
+    for (int64_t e = 0; e < n_elem; e++) {
+        if (elem_mat[e] < 0) { set_error("element %lld has a negative material index", (long long)e); return STAN_E_ARG; }
+        mmax = std::max(mmax, elem_mat[e]);
+    }
+    // every argument is valid: only now is the previous model replaced
     cudaStream_t s = h->stream;
-    h->n_nodes = n_nodes; h->n_elem = n_elem;
+    h->have_mesh = h->have_dof = h->assembled = h->solved = h->recovered = h->postprocessed = false;
+    h->n_nodes = n_nodes; h->n_elem = n_elem; h->n_elem_g2 = n_g2;
     h->h_conn.assign(conn, conn + 8 * n_elem);
     STAN_TRY(h->d_xyz.alloc(3 * n_nodes, s)); STAN_TRY(h->d_conn.alloc(8 * n_elem, s));
     STAN_TRY(h->d_etype.alloc(n_elem, s)); STAN_TRY(h->d_emat.alloc(n_elem, s));
@@ -173,11 +194,8 @@ int stan_set_mesh(stan_handle *h, int64_t n_nodes, const double *xyz, int64_t n_
     STAN_CUDA(cudaMemcpyAsync(h->d_etype.p, elem_type, n_elem, cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaMemcpyAsync(h->d_emat.p, elem_mat, n_elem * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaStreamSynchronize(s));
-    int32_t mmax = 0;
-    for (int64_t e = 0; e < n_elem; e++) { if (elem_mat[e] < 0) { set_error("negative material index"); return STAN_E_ARG; } mmax = std::max(mmax, elem_mat[e]); }
     h->max_mat_index = mmax;
     h->have_mesh = true;
-    h->have_dof = h->assembled = h->solved = h->recovered = h->postprocessed = false;
     h->h_spc_node.clear(); h->h_spc_val.clear(); h->h_load_node.clear(); h->h_load_val.clear();
     return STAN_OK;
 }
@@ -309,11 +327,8 @@ int stan_assemble(stan_handle *h, stan_assembly_stats *stats) {
         stats->nnz_upper = h->nnz_upper;
         // each stored value written once + connectivity/coordinates read once
         stats->assembly_bytes = 72 * h->n_blocks + h->n_elem * 40 + 24 * h->n_nodes;
-        double fl = 0.0;
-        // structured minimum per element: G2 17.3 kflop, G1 2.2 kflop; types are mixed per element
-        // so the caller-visible figure assumes the type of element 0 for the whole mesh
-        fl = (double)h->n_elem * 17300.0;
-        stats->assembly_flops = fl;
+        // structured minimum per element: G2 17.3 kflop, G1 2.2 kflop, by the actual type counts
+        stats->assembly_flops = (double)h->n_elem_g2 * 17300.0 + (double)(h->n_elem - h->n_elem_g2) * 2200.0;
         stats->pattern_ms = t_pat;
         stats->assembly_ms = t_asm;
         stats->total_ms = t_all;
@@ -334,6 +349,25 @@ int stan_solve_cg(stan_handle *h, const stan_cg_options *opts, stan_cg_report *r
     memset(report, 0, sizeof *report);
     h->recovered = h->postprocessed = false;
     return solve_cg(h, opts, report);
+}
+
+int stan_set_cg_history(stan_handle *h, int32_t capacity) {
+    STAN_TRY(check(h));
+    if (capacity < 0) { set_error("stan_set_cg_history: negative capacity"); return STAN_E_ARG; }
+    h->hist_cap = capacity;
+    h->hist_count = 0;
+    return STAN_OK;
+}
+
+int stan_get_cg_history(stan_handle *h, int32_t *count, double *hist4) {
+    STAN_TRY(check(h));
+    if (!h->solved || !count) { set_error("stan_get_cg_history: no CG solve yet or null count"); return STAN_E_STATE; }
+    *count = h->hist_count;
+    if (hist4 && h->hist_count > 0) {
+        STAN_CUDA(cudaMemcpyAsync(hist4, h->d_hist.p, (size_t)4 * h->hist_count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        STAN_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return STAN_OK;
 }
 
 int stan_solve_cholesky(stan_handle *h, stan_chol_report *report) {

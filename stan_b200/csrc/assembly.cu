@@ -480,6 +480,12 @@ int upload_fe_tables() {
     double tab[9 * 24];
     host_fe_tables(tab);
     STAN_CUDA(cudaMemcpyToSymbol(c_dNl, tab, sizeof tab));
+    // constant memory is per device: stan_create calls this for every handle's device
+    unsigned char bi[36], bj[36];
+    int n = 0;
+    for (int i = 0; i < 8; i++) for (int j = i; j < 8; j++) { bi[n] = (unsigned char)i; bj[n] = (unsigned char)j; n++; }
+    STAN_CUDA(cudaMemcpyToSymbol(c_blk_i, bi, sizeof bi));
+    STAN_CUDA(cudaMemcpyToSymbol(c_blk_j, bj, sizeof bj));
     return STAN_OK;
 }
 
@@ -488,15 +494,6 @@ int upload_fe_tables() {
 static int run_assembly_two_kernel(stan_handle *h) {
     cudaStream_t s = h->stream;
     const int64_t nloc = h->row1 - h->row0;
-    static bool tables = false;
-    if (!tables) {
-        unsigned char bi[36], bj[36];
-        int n = 0;
-        for (int i = 0; i < 8; i++) for (int j = i; j < 8; j++) { bi[n] = (unsigned char)i; bj[n] = (unsigned char)j; n++; }
-        STAN_CUDA(cudaMemcpyToSymbol(c_blk_i, bi, sizeof bi));
-        STAN_CUDA(cudaMemcpyToSymbol(c_blk_j, bj, sizeof bj));
-        tables = true;
-    }
     // elements that touch an owned row: all of them on one GPU, a compacted list otherwise
     int64_t n_local = h->n_elem;
     ScratchBuf<int32_t> g2l(&h->scratch[6]), lelem(&h->scratch[7]);
@@ -553,7 +550,7 @@ int run_assembly(stan_handle *h) {
     if (smem > 200 * 1024) {
         set_error("32 consecutive rows couple to %d blocks; the assembly tile holds at most %d", h->max_group_blocks,
                   (int)(200 * 1024 / 72));
-        return STAN_E_CAPACITY;
+        return STAN_E_NOMEM;
     }
     STAN_CUDA(cudaFuncSetAttribute(k_assemble_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_assemble_rows<<<div_up(nloc, ROWS_PER_CTA), ASM_THREADS, smem, s>>>(

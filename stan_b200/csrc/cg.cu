@@ -29,10 +29,19 @@ constexpr int SPMV_WARPS = SPMV_THREADS / 32;
 
 enum ScalarStep { SC_NONE = 0, SC_INIT = 1, SC_AFTER_SPMV = 2, SC_AFTER_UPDATE = 3, SC_AFTER_REFRESH = 4 };
 
-__device__ __forceinline__ void finish_iteration(CgState *st, double cr2, double rznew) {
+// trajectory record of iteration k (stan_get_cg_history); merit = NaN except on refresh iterations
+__device__ __forceinline__ void record_history(CgState *st, int k, double r2, double beta, double merit) {
+    if (st->hist && k >= 1 && k <= st->hist_cap) {
+        double *hrow = st->hist + 4 * (size_t)(k - 1);
+        hrow[0] = r2; hrow[1] = st->alpha; hrow[2] = beta; hrow[3] = merit;
+    }
+}
+
+__device__ __forceinline__ void finish_iteration(CgState *st, double cr2, double rznew, double merit_k) {
     const int k = st->k + 1;
     st->k = k;
     st->r2 = cr2;
+    record_history(st, k, cr2, 0.0, merit_k);
     if (sqrt(cr2) <= st->epsf_bnorm) { st->type = 1; st->done = 1; return; }
     if (st->maxits > 0 && k >= st->maxits) { st->type = 5; st->done = 1; return; }
     const int64_t kk = k - st->counter_off;
@@ -41,6 +50,7 @@ __device__ __forceinline__ void finish_iteration(CgState *st, double cr2, double
         const double uvar = st->rz;
         if (!isfinite(uvar) || uvar == 0.0 || !isfinite(rznew)) { st->type = -4; st->done = 1; return; }
         beta = rznew / uvar;
+        record_history(st, k, cr2, beta, merit_k);
     }
     st->beta = beta;
     st->rz = rznew;
@@ -68,7 +78,7 @@ __device__ void scalar_step(CgState *st, int step) {
             st->alpha = alpha;
         }
     } else if (step == SC_AFTER_UPDATE) {                // partial: [0] = r.r, [1] = r.z
-        finish_iteration(st, st->partial[0], st->partial[1]);
+        finish_iteration(st, st->partial[0], st->partial[1], nan(""));
         if (st->done) st->x_pending = 1;                 // x += alpha p of this iteration rides in k_direction, which now skips
     } else if (step == SC_AFTER_REFRESH) {               // + [2] = 2 b.cx, [3] = (A cx).cx from the SpMV
         st->nmv++;
@@ -77,11 +87,12 @@ __device__ void scalar_step(CgState *st, int step) {
             st->k += 1;
             st->type = 7;
             st->done = 1;
+            record_history(st, st->k, st->r2, 0.0, v1);
             return;
         }
         st->merit = v1;
         st->x_in_alt ^= 1;
-        finish_iteration(st, st->partial[0], st->partial[1]);
+        finish_iteration(st, st->partial[0], st->partial[1], v1);
     }
 }
 
@@ -872,6 +883,11 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     init.restart = restart;
     init.comm = p2p ? comm_dev(h) : nullptr;
     init.red_seq = h->red_seq;              // flags in the peer windows persist across solves
+    if (h->hist_cap > 0) {
+        STAN_TRY(h->d_hist.alloc((size_t)4 * h->hist_cap, s));
+        init.hist = h->d_hist.p;
+        init.hist_cap = h->hist_cap;
+    }
     if (!h->h_state) STAN_CUDA(cudaMallocHost((void **)&h->h_state, sizeof(CgState)));
     CgState *hst = h->h_state;
     *hst = init;
@@ -1002,6 +1018,7 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     // accepted iterate: d_x unless an odd number of refreshes were accepted
     h->x_in_alt = hst->x_in_alt != 0;
     h->red_seq = hst->red_seq;
+    h->hist_count = hst->k < h->hist_cap ? hst->k : h->hist_cap;
     rep->terminationtype = hst->type;
     rep->iterationscount = hst->k;
     rep->nmv = hst->nmv;

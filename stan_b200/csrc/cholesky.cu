@@ -26,6 +26,7 @@ constexpr int ERR_NOT_SPD = 5;   // slot in d_err
 
 struct BandDev {
     double *band;
+    double *diag;                // factored diagonal blocks U_KK, one 64x64 block per block row (see k_chol_panel)
     const int32_t *F;            // first stored block row of block column J
     const int64_t *pofs;         // blocks before block column J
     __device__ __forceinline__ double *blk(int I, int J) const {
@@ -83,7 +84,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 
 // ---- panel: diagonal block Cholesky + row of triangular solves -------------------------------
 // 256 threads.  Every CTA factorises the 64x64 diagonal block (identical arithmetic, so identical
-// bits; cheaper than a second launch per block row) and CTA 0 stores it.  The block lives in
+// bits; cheaper than a second launch per block row) and CTA 0 stores the factor into B.diag[K] — never
+// over A_KK itself, which CTAs of a later wave (grid larger than one resident wave) still have to read.  The block lives in
 // registers: thread (c, q) owns A[q + 4i][c], i < 16.  Step j costs one barrier: the owners publish
 // the raw row j, then every thread scales it by rsqrt(a_jj) itself and applies the rank-1 update to
 // its 16 entries.  The stored diagonal is sqrt(a_jj) exactly; off-diagonals are a_jc * rsqrt(a_jj)
@@ -135,9 +137,10 @@ __global__ void __launch_bounds__(256, 1) k_chol_panel(BandDev B, int K, int m, 
     }
     __syncthreads();
     if (bad && tid == 0 && blockIdx.x == 0) atomicOr(err + ERR_NOT_SPD, 1);
-    if (blockIdx.x == 0)
-        for (int i = tid; i < CBB; i += 256)
-            if ((i >> 6) <= (i & 63)) gkk[i] = D[i];
+    if (blockIdx.x == 0) {
+        double *dkk = B.diag + (int64_t)K * CBB;
+        for (int i = tid; i < CBB; i += 256) dkk[i] = ((i >> 6) <= (i & 63)) ? D[i] : 0.0;
+    }
     __syncthreads();
 
     if (tid >= 224) {                                     // warp 7: forward substitution of the right-hand side
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(256) k_chol_bwd(BandDev B, int J, int cnt, dou
     __shared__ double xs[CB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     pdl_trigger();
-    const double *gjj = B.blk(J, J);
+    const double *gjj = B.diag + (int64_t)J * CBB;
 #pragma unroll
     for (int i = 0; i < CBB / 256; i++) {
         const int e = tid + 256 * i;
@@ -398,28 +401,29 @@ int solve_cholesky(stan_handle *h, stan_chol_report *rep) {
     const double band_bytes = (double)total_blocks * CBB * sizeof(double);
     size_t mem_free = 0, mem_total = 0;
     STAN_CUDA(cudaMemGetInfo(&mem_free, &mem_total));
-    if (band_bytes > 0.95 * (double)mem_total) {
+    if (band_bytes + (double)nbk * CBB * sizeof(double) > 0.95 * (double)mem_total) {
         set_error("stan_solve_cholesky: the skyline needs %.1f GB (%lld blocks of 64x64), the device has %.1f GB; use CG",
                   band_bytes / 1e9, (long long)total_blocks, mem_total / 1e9);
         return STAN_E_NOMEM;
     }
-    DevBuf<double> band, w, y, x;
+    DevBuf<double> band, diag, w, y, x;
     DevBuf<int32_t> dF;
     DevBuf<int64_t> dP;
-    auto free_all = [&]() { band.release(s); w.release(s); y.release(s); x.release(s); dF.release(s); dP.release(s); };
+    auto free_all = [&]() { band.release(s); diag.release(s); w.release(s); y.release(s); x.release(s); dF.release(s); dP.release(s); };
     if (band.alloc((size_t)total_blocks * CBB, s) != STAN_OK) {
         free_all();
         (void)cudaGetLastError();                         // the failed allocation must not poison later calls
         set_error("stan_solve_cholesky: cannot allocate the %.1f GB skyline; use CG", band_bytes / 1e9);
         return STAN_E_NOMEM;
     }
+    STAN_TRY(diag.alloc((size_t)nbk * CBB, s));
     STAN_TRY(w.alloc(npad, s)); STAN_TRY(y.alloc(npad, s)); STAN_TRY(x.alloc(npad, s));
     STAN_TRY(dF.alloc(nbk, s)); STAN_TRY(dP.alloc(nbk + 1, s));
     STAN_CUDA(cudaMemcpyAsync(dF.p, F.data(), nbk * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaMemcpyAsync(dP.p, pofs.data(), (nbk + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaMemsetAsync(band.p, 0, (size_t)total_blocks * CBB * sizeof(double), s));
     STAN_CUDA(cudaMemsetAsync(h->d_err.p + ERR_NOT_SPD, 0, sizeof(int32_t), s));
-    BandDev B{band.p, dF.p, dP.p};
+    BandDev B{band.p, diag.p, dF.p, dP.p};
     k_band_scatter<<<div_up(n, 128), 128, 0, s>>>(nn, h->d_brow_ptr.p, h->d_bcol.p, h->d_vals.p, h->d_fixed.p, B);
     if (npad > n) k_band_pad<<<1, CB, 0, s>>>(n, npad, B);
     STAN_CUDA(cudaMemsetAsync(w.p, 0, npad * sizeof(double), s));
@@ -427,18 +431,18 @@ int solve_cholesky(stan_handle *h, stan_chol_report *rep) {
     int64_t launches = 3;
 
     // ---- factorisation ----
-    static bool attr_set = false;
-    if (!attr_set) {
-        STAN_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * CBB * (int)sizeof(double)));
-        attr_set = true;
-    }
+    // per device and cheap: a process may hold handles on several GPUs
+    STAN_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * CBB * (int)sizeof(double)));
+    const char *tiles_env = getenv("STAN_CHOL_TILES");     // tests force 1 to run panels of more than one wave
+    const int tiles_forced = tiles_env ? atoi(tiles_env) : 0;
     STAN_CUDA(cudaEventRecord(h->ev1, s));
     double flops = 0.0;
     const double b3 = (double)CB * CB * CB;
     static const bool use_pdl = !(getenv("STAN_PDL") && atoi(getenv("STAN_PDL")) == 0);
     for (int64_t K = 0; K < nbk; K++) {
         const int m = E[K] - (int)K;
-        const int tiles = m > 2 * h->sm_count ? 4 : m > h->sm_count ? 2 : 1;
+        const int tiles = (tiles_forced == 1 || tiles_forced == 2 || tiles_forced == 4)
+                              ? tiles_forced : (m > 2 * h->sm_count ? 4 : m > h->sm_count ? 2 : 1);
         STAN_CUDA(launch_step(k_chol_panel, dim3(std::max(1, div_up(m, tiles))), dim3(256), 0, s, use_pdl && K > 0,
                               B, (int)K, m, tiles, w.p, y.p, h->d_err.p));
         launches++;

@@ -130,6 +130,9 @@ struct CgState {
     int32_t x_pending;// 1 when the solve ended at an ordinary iteration whose x += alpha p is still owed
     CommDev *comm;    // peer-memory reductions (multi-GPU P2P mode), else nullptr
     unsigned long long red_seq;   // reductions published so far (same on every rank)
+    double *hist;     // stan_set_cg_history: rows k = 1.. of {||r_k||^2, alpha_k, beta_k, merit or NaN}, else nullptr
+    int32_t hist_cap;
+    int32_t pad0;
 };
 
 struct Comm;  // comm.cu
@@ -149,7 +152,7 @@ struct stan_handle {
     cudaEvent_t stage_ev[2] = {};
 
     // ---- model (global, every rank holds the whole mesh) ----
-    int64_t n_nodes = 0, n_elem = 0;
+    int64_t n_nodes = 0, n_elem = 0, n_elem_g2 = 0;
     int32_t n_mat = 0, max_mat_index = 0;
     bool have_mesh = false, have_mat = false, have_dof = false, assembled = false, solved = false,
          recovered = false;
@@ -194,6 +197,8 @@ struct stan_handle {
     stan::DevBuf<double> d_x, d_xalt, d_r, d_p, d_mv, d_partials;
     stan::DevBuf<stan::CgState> d_state;
     stan::DevBuf<unsigned int> d_counter;
+    stan::DevBuf<double> d_hist;        // 4 doubles per iteration (stan_set_cg_history)
+    int32_t hist_cap = 0, hist_count = 0;
     bool x_in_alt = false;
     unsigned long long red_seq = 0;     // cross-rank reductions published so far (peer-memory mode)
 

@@ -61,14 +61,20 @@ __global__ void k_inc_sort(int64_t nloc, const int32_t *__restrict__ ptr, int32_
 }
 
 // Sorted unique neighbour list of a row (the node itself included).  FILL = false counts.
+// Rows that couple to at most ROW_FAST nodes (every structured hex mesh: 27) are built in registers /
+// local memory by one thread.  A wider row — the reference's hash-table matrix takes any valence
+// (SolverFunctions.cs:123, 162-165) — is appended to `wide_rows` by the count pass and built by
+// k_wide_rows in a global scratch list of 8 candidates per incident element; the fill pass skips it.
+constexpr int ROW_FAST = 96;
+
 template <bool FILL>
 __global__ void k_row_neighbors(int64_t nloc, const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
                                 const int32_t *__restrict__ conn, const int32_t *__restrict__ node_index,
                                 int32_t *__restrict__ cnt, const int32_t *__restrict__ brow_ptr,
-                                int32_t *__restrict__ bcol, int32_t *err) {
+                                int32_t *__restrict__ bcol, int32_t *__restrict__ wide_rows, int32_t *n_wide) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= nloc) return;
-    int32_t nb[STAN_MAX_ROW_BLOCKS];
+    int32_t nb[ROW_FAST];
     int n = 0;
     bool overflow = false;
     for (int t = inc_ptr[p]; t < inc_ptr[p + 1]; t++) {
@@ -81,17 +87,63 @@ __global__ void k_row_neighbors(int64_t nloc, const int32_t *__restrict__ inc_pt
                 if (nb[mid] < q) lo = mid + 1; else hi = mid;
             }
             if (lo < n && nb[lo] == q) continue;
-            if (n == STAN_MAX_ROW_BLOCKS) { overflow = true; continue; }
+            if (n == ROW_FAST) { overflow = true; continue; }
             for (int j = n; j > lo; j--) nb[j] = nb[j - 1];
             nb[lo] = q;
             n++;
         }
     }
-    if (overflow) atomicOr(err, 1);
+    if (overflow) {                                   // list order is irrelevant: every wide row is built on its own
+        if (!FILL) { cnt[p] = 0; wide_rows[atomicAdd(n_wide, 1)] = (int32_t)p; }
+        return;
+    }
     if (!FILL) cnt[p] = n;
     else {
         int32_t *out = bcol + brow_ptr[p];
         for (int j = 0; j < n; j++) out[j] = nb[j];
+    }
+}
+
+__global__ void k_wide_caps(int n_wide, const int32_t *__restrict__ wide_rows, const int32_t *__restrict__ inc_ptr,
+                            int32_t *__restrict__ cap) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_wide) return;
+    cap[i] = i < n_wide ? 8 * (inc_ptr[wide_rows[i] + 1] - inc_ptr[wide_rows[i]]) : 0;
+}
+
+// One warp per wide row.  STAGE 0: gather the 8 nodes of every incident element into the row's scratch
+// segment, sort (odd-even transposition over the warp: the segment is a few hundred entries), drop
+// duplicates in place and publish the count.  STAGE 1 (after the row-pointer scan): copy to bcol.
+template <int STAGE>
+__global__ void k_wide_rows(int n_wide, const int32_t *__restrict__ wide_rows, const int32_t *__restrict__ off,
+                            const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
+                            const int32_t *__restrict__ conn, const int32_t *__restrict__ node_index,
+                            int32_t *__restrict__ scratch, int32_t *__restrict__ cnt,
+                            const int32_t *__restrict__ brow_ptr, int32_t *__restrict__ bcol) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n_wide) return;
+    const int32_t p = wide_rows[w];
+    int32_t *seg = scratch + off[w];
+    if (STAGE == 1) {
+        const int n = cnt[p];
+        for (int j = lane; j < n; j += 32) bcol[brow_ptr[p] + j] = seg[j];
+        return;
+    }
+    const int t0 = inc_ptr[p], m = 8 * (inc_ptr[p + 1] - t0);
+    for (int j = lane; j < m; j += 32) seg[j] = node_index[conn[8 * (int64_t)(inc[t0 + (j >> 3)] >> 3) + (j & 7)]];
+    __syncwarp();
+    for (int round = 0; round < m; round++) {         // odd-even transposition sort, m rounds
+        for (int j = (round & 1) + 2 * lane; j + 1 < m; j += 64) {
+            const int32_t a = seg[j], b = seg[j + 1];
+            if (a > b) { seg[j] = b; seg[j + 1] = a; }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {                                  // unique in place (sequential: runs once per wide row)
+        int n = 0;
+        for (int j = 0; j < m; j++)
+            if (n == 0 || seg[n - 1] != seg[j]) seg[n++] = seg[j];
+        cnt[p] = n;
     }
 }
 
@@ -207,24 +259,47 @@ int build_system_pattern(stan_handle *h) {
     // block rows
     STAN_TRY(h->d_brow_ptr.alloc(nloc + 1 + 4, s));      // +4: the bulk-copy SpMV reads 16-byte granules
     STAN_CUDA(cudaMemsetAsync(cnt.p, 0, (nloc + 1) * sizeof(int32_t), s));
+    ScratchBuf<int32_t> wide(&h->scratch[2]);            // rows wider than ROW_FAST (none on structured meshes)
+    STAN_TRY(wide.alloc(nloc + 1, s));
+    int32_t *n_wide_d = h->d_err.p + 6;                  // zeroed with the error flags above
     k_row_neighbors<false><<<div_up(nloc, 128), 128, 0, s>>>(nloc, h->d_inc_ptr.p, h->d_inc.p, h->d_conn.p,
-                                                             h->d_node_index.p, cnt.p, nullptr, nullptr, h->d_err.p);
+                                                             h->d_node_index.p, cnt.p, nullptr, nullptr, wide.p, n_wide_d);
     STAN_TRY(exclusive_scan(h, cnt.p, h->d_brow_ptr.p, nloc + 1, s));
-    int32_t nblk = 0, herr[4];
+    int32_t nblk = 0, herr[8];
     STAN_CUDA(cudaMemcpyAsync(&nblk, h->d_brow_ptr.p + nloc, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     STAN_CUDA(cudaMemcpyAsync(herr, h->d_err.p, sizeof herr, cudaMemcpyDeviceToHost, s));
     STAN_CUDA(cudaStreamSynchronize(s));
     if (herr[0] & 2) { set_error("dof map is not a permutation of 0..n_nodes-1"); cnt.release(s); return STAN_E_ARG; }
-    if (herr[0] & 1) {
-        set_error("a node couples to more than %d nodes", STAN_MAX_ROW_BLOCKS);
-        cnt.release(s);
-        return STAN_E_CAPACITY;
+    const int n_wide = herr[6];
+    ScratchBuf<int32_t> wcap(&h->scratch[3]), woff(&h->scratch[4]), wscr(&h->scratch[5]);
+    if (n_wide > 0) {
+        STAN_TRY(wcap.alloc(n_wide + 1, s)); STAN_TRY(woff.alloc(n_wide + 1, s));
+        k_wide_caps<<<div_up(n_wide + 1, T), T, 0, s>>>(n_wide, wide.p, h->d_inc_ptr.p, wcap.p);
+        STAN_TRY(exclusive_scan(h, wcap.p, woff.p, n_wide + 1, s));
+        int32_t total = 0;
+        STAN_CUDA(cudaMemcpyAsync(&total, woff.p + n_wide, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        STAN_CUDA(cudaStreamSynchronize(s));
+        STAN_TRY(wscr.alloc(total, s));
+        k_wide_rows<0><<<div_up(32 * (int64_t)n_wide, 128), 128, 0, s>>>(n_wide, wide.p, woff.p, h->d_inc_ptr.p, h->d_inc.p,
+                                                                        h->d_conn.p, h->d_node_index.p, wscr.p, cnt.p,
+                                                                        nullptr, nullptr);
+        STAN_TRY(exclusive_scan(h, cnt.p, h->d_brow_ptr.p, nloc + 1, s));
+        STAN_CUDA(cudaMemcpyAsync(&nblk, h->d_brow_ptr.p + nloc, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        STAN_CUDA(cudaStreamSynchronize(s));
+        h->launches += 4;
     }
     h->n_blocks = nblk;
     STAN_TRY(h->d_bcol.alloc((size_t)nblk + 4, s));
     k_row_neighbors<true><<<div_up(nloc, 128), 128, 0, s>>>(nloc, h->d_inc_ptr.p, h->d_inc.p, h->d_conn.p,
                                                             h->d_node_index.p, nullptr, h->d_brow_ptr.p, h->d_bcol.p,
-                                                            h->d_err.p);
+                                                            nullptr, nullptr);
+    if (n_wide > 0) {
+        k_wide_rows<1><<<div_up(32 * (int64_t)n_wide, 128), 128, 0, s>>>(n_wide, wide.p, woff.p, h->d_inc_ptr.p, h->d_inc.p,
+                                                                        h->d_conn.p, h->d_node_index.p, wscr.p, cnt.p,
+                                                                        h->d_brow_ptr.p, h->d_bcol.p);
+        h->launches += 1;
+    }
+    wide.release(s); wcap.release(s); woff.release(s); wscr.release(s);
     k_group_max<<<div_up(div_up(nloc, 32), T), T, 0, s>>>(nloc, 32, h->d_brow_ptr.p, h->d_err.p + 1);
     k_group_max<<<div_up(div_up(nloc, 16), T), T, 0, s>>>(nloc, 16, h->d_brow_ptr.p, h->d_err.p + 3);
     cnt.release(s);

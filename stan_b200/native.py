@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libstan_b200.so")
 
-OK, E_ARG, E_CUDA, E_SINGULAR, E_STATE, E_CAPACITY, E_DOFMAP, E_COMM, E_NOMEM = 0, -1, -2, -3, -4, -5, -6, -7, -8
+OK, E_ARG, E_CUDA, E_SINGULAR, E_STATE, E_DOFMAP, E_COMM, E_NOMEM = 0, -1, -2, -3, -4, -6, -7, -8
 
 
 class StanError(RuntimeError):
@@ -84,6 +84,8 @@ SYMBOLS = {
     "stan_element_stiffness": (C.c_int, [_P, _I64, _I64, _P]),
     "stan_spmv": (C.c_int, [_P, _P, _P]),
     "stan_time_spmv": (C.c_int, [_P, _I32, C.POINTER(C.c_double), C.POINTER(_I64)]),
+    "stan_set_cg_history": (C.c_int, [_P, _I32]),
+    "stan_get_cg_history": (C.c_int, [_P, C.POINTER(_I32), _P]),
     "stan_kernel_launches": (_I64, [_P]),
     "stan_event_record": (C.c_int, [_P, _I32]),
     "stan_event_elapsed": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_double)]),

@@ -188,6 +188,19 @@ class Solver:
         native.check(self._lib.stan_spmv(self._h, _p(x), _p(y)))
         return y
 
+    def cg_history(self, capacity: int | None = None):
+        """capacity given: arm the recorder for the next LinearSolver_CG; else fetch the (count, 4) record of
+        the last solve: ||r_k||^2, alpha_k, beta_k, energy functional on refresh iterations (NaN otherwise)."""
+        if capacity is not None:
+            native.check(self._lib.stan_set_cg_history(self._h, int(capacity)))
+            return None
+        n = C.c_int32()
+        native.check(self._lib.stan_get_cg_history(self._h, C.byref(n), None))
+        hist = np.empty((n.value, 4))
+        if n.value:
+            native.check(self._lib.stan_get_cg_history(self._h, C.byref(n), _p(hist)))
+        return hist
+
     def time_spmv(self, reps: int = 20):
         ms, by = C.c_double(), C.c_int64()
         native.check(self._lib.stan_time_spmv(self._h, reps, C.byref(ms), C.byref(by)))

@@ -397,6 +397,9 @@ def to_model(db: Database) -> Model:
     node_pos = {n.id: i for i, n in enumerate(db.nodes)}
     mat_pos = {m.id: i for i, m in enumerate(db.mats)}
     types = {"HEX8_G2": HEX8_G2, "HEX8_G1": HEX8_G1}
+    for e in db.elems:
+        if len(e.nlist) != 8:
+            raise ValueError(f"element {e.id} has {len(e.nlist)} nodes; the linear-static path takes hex8 only")
     try:
         conn = np.array([[node_pos[v] for v in e.nlist] for e in db.elems], dtype=np.int32).reshape(-1, 8)
         etype = np.array([types[e.type] for e in db.elems], dtype=np.uint8)
@@ -409,6 +412,8 @@ def to_model(db: Database) -> Model:
         if dst_n is None:
             continue
         for nid, mat in bc.nodal:
+            if nid not in node_pos:
+                raise ValueError(f"BC references missing node {nid}")
             dst_n.append(node_pos[nid])
             dst_v.append((list(mat.M) + [0.0, 0.0, 0.0])[:3])
     a = db.analysis or Analysis()

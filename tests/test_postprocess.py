@@ -39,7 +39,8 @@ def test_load_scalar_matches_oracle(oracle):
     ocell, opoint = PP.load_scalar(m, r.node_index, r.U_full, r.strain, r.stress)
     scale_c = np.abs(ocell).max(axis=(0, 2), keepdims=True) + 1e-30
     scale_p = np.abs(opoint).max(axis=0, keepdims=True) + 1e-30
-    assert np.abs(cell - ocell).max() / 1 <= np.inf                # shapes agree
+    assert cell.shape == ocell.shape == (m.n_elem, 24, 3) and point.shape == opoint.shape == (m.n_nodes, 24)
+    assert cell.dtype == np.float32 and point.dtype == np.float32
     assert (np.abs(cell - ocell) / scale_c).max() < 2e-6           # float32 storage
     assert (np.abs(point - opoint) / scale_p).max() < 2e-6
     assert ms > 0
