@@ -144,13 +144,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    m_dims = mesh.WORKLOADS[args.workload]
+    weak = args.scaling == "weak"
+    m_dims = dict(nx=100, ny=100, nz=500 * args.gpus, elem_type=mesh.HEX8_G2) if weak else mesh.WORKLOADS[args.workload]
+    workload = f"block_weak_{5 * args.gpus}m_g2" if weak else args.workload
     nz = m_dims["nz"]
     full = mesh.Model(xyz=np.zeros((1, 3)), conn=np.zeros((m_dims["nx"] * m_dims["ny"] * nz, 0), np.int32),
                       elem_type=np.array([m_dims["elem_type"]], np.uint8), elem_mat=None, elem_pid=None, mat_E=None,
                       mat_nu=None, spc_node=None, spc_val=None, load_node=None, load_val=None,
                       dims=(m_dims["nx"], m_dims["ny"], nz))
-    iters_full = CG_ITERS_MEASURED.get(args.workload, int(round(CG_ITERS_PER_NZ * nz)))
+    iters_full = CG_ITERS_MEASURED.get(workload, int(round(CG_ITERS_PER_NZ * nz)))
     vals = []
     for i in range(args.warmup + args.steps):
         r = cpu_path_rate(full, iters_full)
@@ -164,14 +166,57 @@ def run_reference(args):
     measured = cpu_measured_100k()
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "elements/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "n_elem": full.n_elem, "cg": "strict EpsF=1e-8"},
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "n_elem": full.n_elem, "cg": "strict EpsF=1e-8"},
             "breakdown": {k: float(np.mean([r[k] for r in vals])) for k in ("assembly_el_s", "cg_iters_s", "recovery_el_s", "spmv_gbs")},
             "cpu_baseline": {"value": v, "unit": "elements/s", "cores": vals[-1]["threads"], "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "measured_100k": measured}
     print(json.dumps(line))
     return 0
+
+
+def weak_model(world: int, tolerance: float = 1e-8):
+    """BASELINE config 5 as a sweep: 5 M elements per GPU, 100 x 100 x (500 N) block in 4 parts along z with
+    alternating Steel / Aluminum (SURVEY.md §8d "Weak scaling"); N = 8 gives the 40 M-element model."""
+    return mesh.beam(100, 100, 500 * world, n_parts=4, tolerance=tolerance)
+
+
+def gpu_measured_100k(Solver):
+    """The same non-extrapolated datapoint the reference arm prints (cpu_measured_100k), on one GPU."""
+    m = mesh.workload("beam_100k_g2", tolerance=1e-8)
+    with Solver() as s:
+        s.SetModel(m); s.AssignDOF()
+        for _ in range(2):                                        # first pass pays pool growth
+            s.event_record(2)
+            s.ParallelAssembly_K(); cg = s.LinearSolver_CG(merit_check=0, IterMax=20000); s.Recovery_Stress()
+            s.event_record(3)
+            ms = s.event_elapsed_ms(2, 3)
+    return {"workload": "beam_100k_g2", "n_elem": m.n_elem, "value": m.n_elem / (ms * 1e-3), "unit": "elements/s",
+            "seconds": ms * 1e-3, "cg_iterations": int(cg.iterationscount), "cg_terminationtype": int(cg.terminationtype),
+            "extrapolated": False}
+
+
+def multi_gpu_parity(Solver, comm_unique_id, dist, local, rank, world):
+    """Outside the timed region: a small jittered multi-part model solved partitioned over all ranks and on one
+    GPU (rank-local), same DOF map, strict CG.  Returns the worst |dU|/|U|, |dS|/|S| and iteration gap over ranks."""
+    import torch
+    m = mesh.beam(12, 10, 16 * world, jitter=True, n_parts=4, tolerance=1e-9)
+    uid = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    with Solver(device=local, rank=rank, world=world) as multi, Solver(device=local) as single:
+        multi.comm_init(uid[0])
+        rm = multi.SolverLinearStatics(m, merit_check=0)
+        rs = single.SolverLinearStatics(m, node_index=rm.node_index, merit_check=0)
+        e0, e1 = multi.element_range()
+        du = float(np.linalg.norm(rm.U_full - rs.U_full) / np.linalg.norm(rs.U_full))
+        ds = float(np.abs(rm.stress - rs.stress[e0:e1]).max() / np.abs(rs.stress).max())
+        its = abs(int(rm.cg.iterationscount) - int(rs.cg.iterationscount))
+        ok = rm.cg.terminationtype == 1 and rs.cg.terminationtype == 1
+    t = torch.tensor([du, ds, float(its), 0.0 if ok else 1.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"model": f"12x10x{16 * world} jittered, 4 parts / 2 materials, strict EpsF=1e-9", "du": float(t[0]), "ds": float(t[1]),
+            "its_gap": int(t[2]), "converged": bool(t[3] == 0.0), "against": "single-GPU solve of the same model on each rank's device"}
 
 
 def run_ours(args):
@@ -194,16 +239,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    m = mesh.workload(args.workload, tolerance=1e-8)
-    s = Solver(device=local, rank=rank, world=world)
+    weak = args.scaling == "weak"
+    workload = f"block_weak_{5 * world}m_g2" if weak else args.workload
+    m = weak_model(world) if weak else mesh.workload(args.workload, tolerance=1e-8)
+    s = Solver(device=local, rank=rank, world=world, pinned_results=True)
     if world > 1:
         uid = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         s.comm_init(uid[0])
+    m = s.pinned_model(m)                                 # inputs wait in page-locked host memory (bench contract)
     s.SetModel(m)
     t0 = time.perf_counter()
     ni = s.AssignDOF()                                    # R0 (Database.cs:140-234), device BFS at this size; not in the step
     t_dof = time.perf_counter() - t0
+    ni_pinned = s.pinned_empty(ni.shape, ni.dtype)
+    ni_pinned[...] = ni
 
     call_wall = []                                        # host wall time of the three calls, per step
 
@@ -240,35 +290,59 @@ def run_ours(args):
     call_ms = {"assemble": float(tmax[2]), "solve": float(tmax[3]), "recover": float(tmax[4])}
 
     # ---- end to end through the C ABI with host buffers (H2D + D2H inside the timed region) ----
+    # Every step uploads the model and the DOF map from page-locked host arrays and downloads the results into
+    # page-locked arrays: on one GPU U (DOF order), the per-node displacements and all strains / stresses; on
+    # several GPUs each rank its own rows of U and its slice of the strains / stresses (no rank downloads what
+    # another rank also downloads: d2h is independent of N).
     h2d = m.xyz.nbytes + m.conn.nbytes + m.elem_type.nbytes + m.elem_mat.nbytes + ni.nbytes + m.spc_node.nbytes \
         + m.spc_val.nbytes + m.load_node.nbytes + m.load_val.nbytes + m.mat_E.nbytes + m.mat_nu.nbytes
-    # every rank downloads the full displacement vector and the strain/stress of its element slice
-    d2h = world * m.n_dof * 8 + 2 * 48 * m.n_elem * 8
+    tip = ni[m.load_node]                                 # rows of the loaded (tip) nodes
+
+    def e2e_pass():
+        r = s.SolverLinearStatics(m, node_index=ni_pinned, merit_check=0, local_rows=world > 1)
+        if world > 1:
+            r0, r1 = s.partition()
+            mine = tip[(tip >= r0) & (tip < r1)] - r0
+            chk = float(np.abs(r.U_full[mine]).max()) if mine.size else 0.0
+            nbytes = r.U_full.nbytes + r.strain.nbytes + r.stress.nbytes
+        else:
+            chk = float(np.abs(r.disp[m.load_node]).max())
+            nbytes = r.U_full.nbytes + r.disp.nbytes + r.strain.nbytes + r.stress.nbytes
+        return chk, nbytes
+
+    e2e_pass()                                            # untimed: result buffers allocated and touched
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
-        r = s.SolverLinearStatics(m, node_index=ni, merit_check=0)
-        chk = float(np.abs(r.U_full).max())
+        chk, d2h_rank = e2e_pass()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / max(args.e2e_steps, 1)
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    te = torch.tensor([e2e_ms, chk], dtype=torch.float64, device="cuda")
+    td = torch.tensor([float(d2h_rank)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te[0])
+        dist.all_reduce(td, op=dist.ReduceOp.SUM)
+    e2e_ms, chk, d2h = float(te[0]), float(te[1]), int(td[0])
 
     a, cg, rc = recs[-1]
     peak, peak_src = measured_peaks()
     spmv_ms = cg.spmv_ms / max(cg.spmv_launches, 1)
     achieved = cg.spmv_bytes / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
+    # slowest rank's SpMV decides the iteration: report the minimum achieved bandwidth over ranks
+    ta = torch.tensor([-achieved], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+    achieved_min = -float(ta[0])
     traffic = None
     tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.workload, {}).get(str(world))
+        traffic = json.load(open(tp)).get(args.workload if not weak else "weak", {}).get(str(world))
+    parity = multi_gpu_parity(Solver, comm_unique_id, dist, local, rank, world) if world > 1 else None
     line = {
         "metric": METRIC, "value": m.n_elem / (dev_ms * 1e-3), "unit": "elements/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "n_elem": m.n_elem, "n_dof": m.n_dof, "cg": "strict EpsF=1e-8 (merit check off)",
+        "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "n_elem": m.n_elem, "n_dof": m.n_dof, "cg": "strict EpsF=1e-8 (merit check off)",
                    "parallelism": f"node-range partition x{world}", "l2": "inputs (matrix 72 B/block) far exceed the 126 MB L2",
                    "timing": "CUDA events on the library stream, max over ranks"},
         "breakdown": {"assembly_el_s": m.n_elem / (a.total_ms * 1e-3), "ke_kernel_el_s": m.n_elem / (a.assembly_ms * 1e-3),
@@ -277,18 +351,23 @@ def run_ours(args):
                       "cg_rel_residual": float(np.sqrt(cg.r2) / cg.bnorm) if cg.bnorm else 0.0,
                       "cg_iters_s": cg.iterationscount / (cg.solve_ms * 1e-3), "cg_solve_ms": cg.solve_ms,
                       "cg_iter_gbs": cg.iter_bytes * cg.iterationscount / (cg.solve_ms * 1e-3) / 1e9,
-                      "spmv_gbs": achieved, "spmv_ms": spmv_ms, "recovery_el_s": m.n_elem / (rc.recover_ms * 1e-3),
+                      "spmv_gbs": achieved_min, "spmv_ms": spmv_ms, "recovery_el_s": m.n_elem / (rc.recover_ms * 1e-3),
                       "recovery_gbs": rc.recover_bytes / (rc.recover_ms * 1e-3) / 1e9, "assign_dof_s": t_dof,
                       "wall_ms_per_step": wall_ms, "call_wall_ms_max_over_ranks": call_ms},
-        "roofline": {"kernel": "k_spmv (block-row CSR SpMV + p.Ap)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "bytes_per_launch": cg.spmv_bytes},
-        "e2e": {"value": m.n_elem / (e2e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": args.e2e_steps, "check_max_abs_u": chk},
+        "roofline": {"kernel": "k_spmv_tile3 (block-row CSR SpMV + p.Ap" + (", halo exchange fused)" if world > 1 else ")"),
+                     "bound": "hbm", "achieved": achieved_min, "peak": peak,
+                     "unit": "GB/s", "frac": achieved_min / peak, "traffic": traffic, "peak_source": peak_src,
+                     "bytes_per_launch": cg.spmv_bytes, "ranks": "minimum over ranks" if world > 1 else "single GPU"},
+        "e2e": {"value": m.n_elem / (e2e_ms * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": int(h2d) * world,
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms, "steps": args.e2e_steps, "check_max_abs_u": chk,
+                "host_memory": "page-locked (stan_host_alloc) inputs and result buffers"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if parity is not None:
+        line["parity"] = parity
     if rank == 0:
         if not args.no_cpu:
+            line["breakdown"]["measured_100k"] = gpu_measured_100k(Solver)
             c = cpu_path_rate(m, cg.iterationscount)
             line["cpu_baseline"] = {
                 "value": c["value"], "unit": "elements/s", "cores": c["threads"], "kind": "port",
@@ -313,6 +392,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cg-maxits", type=int, default=20000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="weak: 5 M elements per GPU, 100x100x(500 N) multi-part block (BASELINE config 5 sweep)")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 

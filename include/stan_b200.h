@@ -18,6 +18,7 @@
 #ifndef STAN_B200_H
 #define STAN_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -150,6 +151,12 @@ int stan_recover(stan_handle *h, stan_recovery_stats *stats);
 /* --- results: what Solver.cs:171-178,203-210 writes back into Node / Element --------------- */
 /* U_Full[nDOF] indexed by DOF (zeros at fixed DOFs). */
 int stan_get_displacements(stan_handle *h, double *u_full);
+/* The rows this rank owns, [first_row, last_row) of stan_get_partition, 3 doubles per row: what a caller that
+ * merges the ranks' results itself downloads instead of the whole vector (same as stan_get_displacements on one GPU). */
+int stan_get_displacements_local(stan_handle *h, double *u_rows);
+/* Node.dU_buffer for every node in NodeLib order (Solver.cs:171-178: dU_buffer[i] = U_Full[DOF[i]]), n_nodes x 3;
+ * the gather through the DOF map runs on the device. */
+int stan_get_node_displacements(stan_handle *h, double *disp);
 /* Element.Strain[1] / Stress[1]: 8 x 6 row-major per element, for the elements [first, last) of
  * stan_get_element_range — all of ElemLib on one GPU, this rank's contiguous slice otherwise. */
 int stan_get_strain_stress(stan_handle *h, double *strain, double *stress);
@@ -163,6 +170,11 @@ int stan_get_element_range(stan_handle *h, int64_t *first, int64_t *last);
  * (stan_get_partition) in DOF-map order: point[r - first_row] belongs to the node with DOF[0]/3 == r. */
 int stan_postprocess(stan_handle *h, double *device_ms);
 int stan_get_scalars(stan_handle *h, float *cell, float *point);
+
+/* Page-locked host memory for callers that want the copies at the boundary to be plain DMA transfers (any
+ * host pointer is accepted everywhere; pageable memory goes through the library's staging buffers). */
+int stan_host_alloc(size_t bytes, void **out);
+int stan_host_free(void *p);
 
 /* --- parity / inspection (SURVEY §8b "optional") ------------------------------------------- */
 int stan_get_dof_reduction(stan_handle *h, int32_t *ndof_reduction);          /* Solver.cs:121-132 */

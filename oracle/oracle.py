@@ -164,6 +164,14 @@ class UpperCsr:
         fn.restype = C.c_void_p
         return cls(fn(C.c_int64(n), _p(rp), _p(col), _p(val)), 0)
 
+    @classmethod
+    def from_arrays(cls, rowptr, col, val):
+        """Wraps an upper-triangle CRS given as arrays (e.g. the one libstan_b200 exports) for lincg / sym_spmv."""
+        rp, c, v = np.ascontiguousarray(rowptr, np.int64), np.ascontiguousarray(col, np.int32), _f64(val)
+        fn = lib().stan_oracle_csr_from_arrays
+        fn.restype = C.c_void_p
+        return cls(fn(C.c_int64(len(rp) - 1), _p(rp), _p(c), _p(v)), 0)
+
     def arrays(self):
         if self._arrays is None:
             rp = np.zeros(self.n + 1, dtype=np.int64)

@@ -30,10 +30,16 @@ static int check(stan_handle *h) {
 // Large results go to the caller's (pageable, usually untouched) buffer through two pinned staging
 // buffers: the DMA engine fills one while several host threads copy the other out — first-touch page
 // faults on the destination are what bound a plain cudaMemcpy to ~4 GB/s.
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 static int copy_to_host(stan_handle *h, void *dst, const void *d_src, size_t bytes) {
     cudaStream_t s = h->stream;
     const size_t CH = (size_t)64 << 20;
-    if (bytes < 2 * CH) {
+    if (bytes < 2 * CH || is_pinned(dst)) {          // page-locked destination (stan_host_alloc): one DMA, no staging
         STAN_CUDA(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, s));
         STAN_CUDA(cudaStreamSynchronize(s));
         return STAN_OK;
@@ -70,15 +76,80 @@ static int copy_to_host(stan_handle *h, void *dst, const void *d_src, size_t byt
     return STAN_OK;
 }
 
-static int upload_dof_map(stan_handle *h, const int32_t *node_index) {
+// The model is checked where it lands: a pass over 80 M connectivity entries costs the host ~0.1 s and the
+// device ~0.1 ms.  res[0..2] = first element with a bad node index / type / material index, res[3] = largest
+// material index, res[4] = number of HEX8_G2 elements.
+__global__ void k_check_mesh(long long n_elem, long long n_nodes, const int32_t *__restrict__ conn,
+                             const uint8_t *__restrict__ etype, const int32_t *__restrict__ emat, long long *res) {
+    const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool in = e < n_elem;
+    bool g2 = false;
+    if (in) {
+        const int4 c0 = *reinterpret_cast<const int4 *>(conn + 8 * e), c1 = *reinterpret_cast<const int4 *>(conn + 8 * e + 4);
+        const int lo = min(min(min(c0.x, c0.y), min(c0.z, c0.w)), min(min(c1.x, c1.y), min(c1.z, c1.w)));
+        const int hi = max(max(max(c0.x, c0.y), max(c0.z, c0.w)), max(max(c1.x, c1.y), max(c1.z, c1.w)));
+        if (lo < 0 || hi >= n_nodes) atomicMin((unsigned long long *)&res[0], (unsigned long long)e);
+        const int t = etype[e];
+        if (t != STAN_HEX8_G1 && t != STAN_HEX8_G2) atomicMin((unsigned long long *)&res[1], (unsigned long long)e);
+        g2 = t == STAN_HEX8_G2;
+        const int m = emat[e];
+        if (m < 0) atomicMin((unsigned long long *)&res[2], (unsigned long long)e);
+        else if (m > 0) atomicMax((unsigned long long *)&res[3], (unsigned long long)m);
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, g2);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd((unsigned long long *)&res[4], (unsigned long long)__popc(b));
+}
+
+// node_index must be a permutation of 0..n-1: scatter the inverse, then look for holes (a duplicate leaves one)
+__global__ void k_perm_scatter(long long n, const int32_t *__restrict__ node_index, int32_t *__restrict__ inv, long long *bad) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t p = node_index[i];
+    if (p < 0 || p >= n) atomicMin((unsigned long long *)bad, (unsigned long long)i);
+    else inv[p] = (int32_t)i;
+}
+__global__ void k_perm_holes(long long n, const int32_t *__restrict__ inv, long long *bad) {
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p < n && inv[p] < 0) atomicMin((unsigned long long *)(bad + 1), (unsigned long long)p);
+}
+
+__global__ void k_gather_rows3(long long n, const int32_t *__restrict__ node_index, const double *__restrict__ ufull,
+                               double *__restrict__ out) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= 3 * n) return;
+    const long long i = t / 3;
+    out[t] = ufull[3 * (long long)node_index[i] + (t - 3 * i)];
+}
+
+// d_node_index holds the candidate map; verifies it on the device and leaves the inverse in d_inv
+static int check_dof_map(stan_handle *h) {
     cudaStream_t s = h->stream;
-    h->h_node_index.assign(node_index, node_index + h->n_nodes);
-    STAN_TRY(h->d_node_index.alloc(h->n_nodes, s));
-    STAN_CUDA(cudaMemcpyAsync(h->d_node_index.p, h->h_node_index.data(), h->n_nodes * sizeof(int32_t),
-                              cudaMemcpyHostToDevice, s));
+    const int64_t n = h->n_nodes;
+    STAN_TRY(h->d_inv.alloc(n, s));
+    ScratchBuf<long long> bad(&h->scratch[9]);
+    STAN_TRY(bad.alloc(2, s));
+    STAN_CUDA(cudaMemsetAsync(h->d_inv.p, 0xff, n * sizeof(int32_t), s));
+    STAN_CUDA(cudaMemsetAsync(bad.p, 0x7f, 2 * sizeof(long long), s));
+    k_perm_scatter<<<div_up(n, 256), 256, 0, s>>>(n, h->d_node_index.p, h->d_inv.p, bad.p);
+    k_perm_holes<<<div_up(n, 256), 256, 0, s>>>(n, h->d_inv.p, bad.p);
+    long long hb[2];
+    STAN_CUDA(cudaMemcpyAsync(hb, bad.p, sizeof hb, cudaMemcpyDeviceToHost, s));
     STAN_CUDA(cudaStreamSynchronize(s));
-    h->have_dof = true;
+    h->launches += 2;
+    if (hb[0] < n) { set_error("dof map is not a permutation (node %lld maps outside [0,%lld))", hb[0], (long long)n); return STAN_E_ARG; }
+    if (hb[1] < n) { set_error("dof map is not a permutation (no node maps to index %lld)", hb[1]); return STAN_E_ARG; }
+    return STAN_OK;
+}
+
+static int upload_dof_map(stan_handle *h, const int32_t *node_index, bool verify) {
+    cudaStream_t s = h->stream;
+    h->have_dof = false;
     h->assembled = h->solved = h->recovered = h->postprocessed = false;
+    STAN_TRY(h->d_node_index.alloc(h->n_nodes, s));
+    STAN_CUDA(cudaMemcpyAsync(h->d_node_index.p, node_index, h->n_nodes * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (verify) STAN_TRY(check_dof_map(h));
+    else STAN_CUDA(cudaStreamSynchronize(s));
+    h->have_dof = true;
     return STAN_OK;
 }
 
@@ -164,37 +235,42 @@ int stan_set_mesh(stan_handle *h, int64_t n_nodes, const double *xyz, int64_t n_
         set_error("stan_set_mesh: empty mesh or null array"); return STAN_E_ARG;
     }
     if (3 * n_nodes > INT32_MAX) { set_error("more than %d DOFs", INT32_MAX); return STAN_E_ARG; }
-    for (int64_t i = 0; i < 8 * n_elem; i++)
-        if (conn[i] < 0 || conn[i] >= n_nodes) {
-            set_error("element %lld references node %d outside [0,%lld)", (long long)(i / 8), conn[i], (long long)n_nodes);
-            return STAN_E_ARG;
-        }
-    int64_t n_g2 = 0;
-    for (int64_t e = 0; e < n_elem; e++) {
-        if (elem_type[e] != STAN_HEX8_G1 && elem_type[e] != STAN_HEX8_G2) {
-            set_error("element %lld has unsupported type %d (only HEX8_G1/HEX8_G2)", (long long)e, (int)elem_type[e]);
-            return STAN_E_ARG;
-        }
-        n_g2 += elem_type[e] == STAN_HEX8_G2;
-    }
-    int32_t mmax = 0;
-    for (int64_t e = 0; e < n_elem; e++) {
-        if (elem_mat[e] < 0) { set_error("element %lld has a negative material index", (long long)e); return STAN_E_ARG; }
-        mmax = std::max(mmax, elem_mat[e]);
-    }
-    // every argument is valid: only now is the previous model replaced
+    // Upload first, check on the device, and only then replace the previous model: a rejected call leaves the
+    // handle without a mesh rather than with a half-updated one.
     cudaStream_t s = h->stream;
     h->have_mesh = h->have_dof = h->assembled = h->solved = h->recovered = h->postprocessed = false;
-    h->n_nodes = n_nodes; h->n_elem = n_elem; h->n_elem_g2 = n_g2;
-    h->h_conn.assign(conn, conn + 8 * n_elem);
+    h->h_conn.clear(); h->h_conn.shrink_to_fit();
     STAN_TRY(h->d_xyz.alloc(3 * n_nodes, s)); STAN_TRY(h->d_conn.alloc(8 * n_elem, s));
     STAN_TRY(h->d_etype.alloc(n_elem, s)); STAN_TRY(h->d_emat.alloc(n_elem, s));
     STAN_CUDA(cudaMemcpyAsync(h->d_xyz.p, xyz, 3 * n_nodes * sizeof(double), cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaMemcpyAsync(h->d_conn.p, conn, 8 * n_elem * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaMemcpyAsync(h->d_etype.p, elem_type, n_elem, cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaMemcpyAsync(h->d_emat.p, elem_mat, n_elem * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ScratchBuf<long long> res(&h->scratch[9]);
+    STAN_TRY(res.alloc(5, s));
+    const long long init[5] = {INT64_MAX, INT64_MAX, INT64_MAX, 0, 0};
+    STAN_CUDA(cudaMemcpyAsync(res.p, init, sizeof init, cudaMemcpyHostToDevice, s));
+    k_check_mesh<<<div_up(n_elem, 256), 256, 0, s>>>(n_elem, n_nodes, h->d_conn.p, h->d_etype.p, h->d_emat.p, res.p);
+    long long r[5];
+    STAN_CUDA(cudaMemcpyAsync(r, res.p, sizeof r, cudaMemcpyDeviceToHost, s));
     STAN_CUDA(cudaStreamSynchronize(s));
-    h->max_mat_index = mmax;
+    STAN_CUDA(cudaGetLastError());
+    h->launches += 1;
+    if (r[0] < n_elem) {
+        const int32_t *c = conn + 8 * r[0];
+        int32_t badv = c[0];
+        for (int k = 0; k < 8; k++) if (c[k] < 0 || c[k] >= n_nodes) { badv = c[k]; break; }
+        set_error("element %lld references node %d outside [0,%lld)", r[0], badv, (long long)n_nodes);
+        return STAN_E_ARG;
+    }
+    if (r[1] < n_elem) {
+        set_error("element %lld has unsupported type %d (only HEX8_G1/HEX8_G2)", r[1], (int)elem_type[r[1]]);
+        return STAN_E_ARG;
+    }
+    if (r[2] < n_elem) { set_error("element %lld has a negative material index", r[2]); return STAN_E_ARG; }
+    h->n_nodes = n_nodes; h->n_elem = n_elem; h->n_elem_g2 = r[4];
+    h->max_mat_index = (int32_t)r[3];
+    h->nnz_upper = 0;
     h->have_mesh = true;
     h->h_spc_node.clear(); h->h_spc_val.clear(); h->h_load_node.clear(); h->h_load_val.clear();
     return STAN_OK;
@@ -225,13 +301,7 @@ int stan_set_dof_map(stan_handle *h, const int32_t *node_index) {
     STAN_TRY(check(h));
     if (!h->have_mesh) { set_error("stan_set_dof_map before stan_set_mesh"); return STAN_E_STATE; }
     if (!node_index) { set_error("null dof map"); return STAN_E_ARG; }
-    std::vector<uint8_t> seen((size_t)h->n_nodes, 0);
-    for (int64_t i = 0; i < h->n_nodes; i++) {
-        int32_t p = node_index[i];
-        if (p < 0 || p >= h->n_nodes || seen[p]) { set_error("dof map is not a permutation (node %lld -> %d)", (long long)i, p); return STAN_E_ARG; }
-        seen[p] = 1;
-    }
-    return upload_dof_map(h, node_index);
+    return upload_dof_map(h, node_index, true);
 }
 
 int stan_assign_dof(stan_handle *h, int32_t *node_index_out) {
@@ -247,9 +317,16 @@ int stan_assign_dof(stan_handle *h, int32_t *node_index_out) {
         STAN_TRY(assign_dof_device(h, ni.data(), &narrow));
         on_device = !narrow;
     }
-    if (!on_device) STAN_TRY(assign_dof_host(h->n_nodes, h->n_elem, h->h_conn.data(), ni.data()));
+    if (!on_device) {
+        if (h->h_conn.empty()) {                           // host copy of the connectivity, only when this path needs it
+            h->h_conn.resize((size_t)8 * h->n_elem);
+            STAN_CUDA(cudaMemcpyAsync(h->h_conn.data(), h->d_conn.p, h->h_conn.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            STAN_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        STAN_TRY(assign_dof_host(h->n_nodes, h->n_elem, h->h_conn.data(), ni.data()));
+    }
     if (node_index_out) memcpy(node_index_out, ni.data(), ni.size() * sizeof(int32_t));
-    return upload_dof_map(h, ni.data());
+    return upload_dof_map(h, ni.data(), false);
 }
 
 int stan_set_spc(stan_handle *h, int64_t n, const int32_t *node, const double *val3) {
@@ -392,6 +469,40 @@ int stan_get_displacements(stan_handle *h, double *u_full) {
     return copy_to_host(h, u_full, h->d_ufull.p, 3 * h->n_nodes * sizeof(double));
 }
 
+int stan_get_displacements_local(stan_handle *h, double *u_rows) {
+    STAN_TRY(check(h));
+    if (!h->solved) { set_error("no solution yet"); return STAN_E_STATE; }
+    if (!u_rows) { set_error("null output"); return STAN_E_ARG; }
+    return copy_to_host(h, u_rows, h->sol, (size_t)3 * (h->row1 - h->row0) * sizeof(double));
+}
+
+int stan_get_node_displacements(stan_handle *h, double *disp) {
+    STAN_TRY(check(h));
+    if (!h->solved) { set_error("no solution yet"); return STAN_E_STATE; }
+    if (!disp) { set_error("null output"); return STAN_E_ARG; }
+    if (!h->recovered) STAN_TRY(scatter_solution(h));
+    cudaStream_t s = h->stream;
+    DevBuf<double> tmp;
+    STAN_TRY(tmp.alloc((size_t)3 * h->n_nodes, s));
+    k_gather_rows3<<<div_up(3 * h->n_nodes, 256), 256, 0, s>>>(h->n_nodes, h->d_node_index.p, h->d_ufull.p, tmp.p);
+    h->launches += 1;
+    const int rc = copy_to_host(h, disp, tmp.p, (size_t)3 * h->n_nodes * sizeof(double));
+    tmp.release(s);
+    return rc;
+}
+
+int stan_host_alloc(size_t bytes, void **out) {
+    if (!out) { set_error("null out pointer"); return STAN_E_ARG; }
+    *out = nullptr;
+    STAN_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return STAN_OK;
+}
+
+int stan_host_free(void *p) {
+    if (p) STAN_CUDA(cudaFreeHost(p));
+    return STAN_OK;
+}
+
 int stan_get_strain_stress(stan_handle *h, double *strain, double *stress) {
     STAN_TRY(check(h));
     if (!h->recovered) { set_error("stan_get_strain_stress before stan_recover"); return STAN_E_STATE; }
@@ -447,7 +558,7 @@ int stan_get_rhs(stan_handle *h, double *F_reduced) {
 int stan_get_solution_reduced(stan_handle *h, double *U_reduced) {
     STAN_TRY(check(h));
     if (!h->solved) { set_error("no solution yet"); return STAN_E_STATE; }
-    return reduced_from_full(h, h->x_in_alt ? h->d_xalt.p : h->d_x.p, U_reduced);
+    return reduced_from_full(h, h->sol, U_reduced);
 }
 
 int stan_get_csr_upper_size(stan_handle *h, int64_t *n, int64_t *nnz) {

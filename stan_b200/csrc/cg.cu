@@ -96,39 +96,66 @@ __device__ void scalar_step(CgState *st, int step) {
     }
 }
 
-// Multi-GPU, peer-memory mode: the thread that holds this rank's partial sums writes them into every
-// peer's window over NVLink, raises a sequence flag, waits for the peers' flags and adds the W
-// contributions in rank order — every rank obtains bitwise identical sums, so all ranks take the
-// same branches.  Slots are double-buffered by sequence parity; a rank cannot be two reductions ahead
-// of a peer because each reduction needs that peer's contribution.
-__device__ void cross_rank_sum(CgState *st, int cnt) {
+// Multi-GPU, peer-memory mode: warp 0 of the CTA that holds this rank's partial sums exchanges them with every
+// peer over NVLink and adds the W contributions in rank order — every rank obtains bitwise identical sums, so
+// all ranks take the same branches.  Lane r talks to rank r.  A double travels as two 8-byte words, each
+// carrying 32 payload bits and the 32-bit sequence tag of this reduction: an aligned 8-byte store arrives
+// whole, so the reader needs no separate flag and the writer no fence between payload and flag — one NVLink
+// one-way latency per reduction.  Slots are double-buffered by sequence parity; a rank cannot be two reductions
+// ahead of a peer because each reduction needs that peer's contribution.
+__device__ __forceinline__ void st_volatile_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ void cross_rank_sum(CgState *st, int cnt, int lane) {
     CommDev *cd = st->comm;
     const int W = cd->world, me = cd->rank;
-    const unsigned long long seq = ++st->red_seq;
+    const unsigned long long seq = st->red_seq + 1;
     const int par = (int)(seq & 1);
-    for (int r = 0; r < W; r++) {
-        if (r == me) continue;
-        for (int i = 0; i < cnt; i++) cd->ctrl[r]->red[par][me][i] = st->partial[i];
+    const unsigned long long tag = ((seq % 0xffffffffull) + 1) << 32;     // never 0: a fresh window is all zeros
+    double mine[4];
+    for (int i = 0; i < 4; i++) mine[i] = i < cnt ? st->partial[i] : 0.0;
+    if (lane < W && lane != me)
+        for (int i = 0; i < cnt; i++) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(mine[i]);
+            unsigned long long *dst = cd->ctrl[lane]->red[par][me][i];
+            st_volatile_u64(dst, (bits & 0xffffffffull) | tag);
+            st_volatile_u64(dst + 1, (bits >> 32) | tag);
+        }
+    double got[4] = {0.0, 0.0, 0.0, 0.0};
+    bool timed_out = false;
+    if (lane < W) {
+        if (lane == me) {
+            for (int i = 0; i < 4; i++) got[i] = mine[i];
+        } else {
+            const long long t0 = clock64();
+            for (int i = 0; i < cnt && !timed_out; i++) {
+                const unsigned long long *src = cd->ctrl[me]->red[par][lane][i];
+                unsigned long long w0, w1;
+                for (;;) {
+                    w0 = ld_volatile_u64(src); w1 = ld_volatile_u64(src + 1);
+                    if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) break;
+                    if (clock64() - t0 > 8000000000LL) { timed_out = true; break; }       // ~4 s: a peer died
+                }
+                got[i] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+            }
+        }
     }
-    __threadfence_system();
-    for (int r = 0; r < W; r++)
-        if (r != me) *(volatile unsigned long long *)&cd->ctrl[r]->rflag[par][me] = seq;
+    const bool any_timeout = __any_sync(0xffffffffu, timed_out);
     double sum[4] = {0.0, 0.0, 0.0, 0.0};
-    P2PCtrl *mine = cd->ctrl[me];
-    for (int r = 0; r < W; r++) {
-        if (r == me) {
-            for (int i = 0; i < cnt; i++) sum[i] += st->partial[i];
-            continue;
-        }
-        volatile unsigned long long *f = &mine->rflag[par][r];
-        const long long t0 = clock64();
-        while (*f < seq) {
-            if (clock64() - t0 > 8000000000LL) { atomicOr(cd->err + 4, 1); st->type = -4; st->done = 1; return; }
-        }
-        __threadfence_system();
-        for (int i = 0; i < cnt; i++) sum[i] += __ldcg(&mine->red[par][r][i]);
+    for (int r = 0; r < W; r++)
+        for (int i = 0; i < 4; i++) sum[i] += __shfl_sync(0xffffffffu, got[i], r);     // rank order, same on every rank
+    if (lane == 0) {
+        if (any_timeout) { atomicOr(cd->err + 4, 1); st->type = -4; st->done = 1; }
+        for (int i = 0; i < cnt; i++) st->partial[i] = sum[i];
+        st->red_seq = seq;
     }
-    for (int i = 0; i < cnt; i++) st->partial[i] = sum[i];
+    __syncwarp();
 }
 
 __global__ void k_scalar(CgState *st, int step) {
@@ -138,8 +165,9 @@ __global__ void k_scalar(CgState *st, int step) {
 
 // Block-level sum of NV values, published to partials[]; the last CTA to arrive folds all CTA
 // partials in a fixed order into st->partial[slot0..] and (single GPU) runs the scalar step.
+// Returns true in every thread of the last CTA.
 template <int NV>
-__device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partials, unsigned int *counter, CgState *st,
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials, unsigned int *counter, CgState *st,
                                             int slot0, int step, bool run_scalar) {
     __shared__ double s_red[NV][32];
     __shared__ bool s_last;
@@ -167,7 +195,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partials, u
         s_last = (ticket == gridDim.x - 1);
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) return false;
     __threadfence();
     double acc[NV];
 #pragma unroll
@@ -192,11 +220,13 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double *partials, u
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             if (lane == 0) st->partial[slot0 + i] = x;
         }
-        if (lane == 0 && run_scalar && step != SC_NONE) {
-            if (st->comm) cross_rank_sum(st, step == SC_AFTER_REFRESH ? 4 : (step == SC_AFTER_SPMV ? 1 : 2));
-            if (!st->done) scalar_step(st, step);
+        if (run_scalar && step != SC_NONE) {
+            __syncwarp();
+            if (st->comm) cross_rank_sum(st, step == SC_AFTER_REFRESH ? 4 : (step == SC_AFTER_SPMV ? 1 : 2), lane);
+            if (lane == 0 && !st->done) scalar_step(st, step);
         }
     }
+    return true;
 }
 
 // ---- SpMV -----------------------------------------------------------------------------------
@@ -523,55 +553,114 @@ constexpr int T3_ROWS = 32, T3_PARTS = 3, T3_GROUPS = 3;
 constexpr int T3_GW = 3 * T3_PARTS;                       // warps per group
 constexpr int T3_THREADS = 32 * (T3_GROUPS * T3_GW + 1);
 
-template <bool DOT>
+// HALO = true (several GPUs, peer-memory mode) adds the halo exchange of the input vector to the product itself:
+//  * tiles are taken in the order of ha.tile_order — the ones whose rows have no halo column first;
+//  * the producer warp, once the first ring stages are in flight, stores this rank's boundary entries of x into
+//    the halo tails of the neighbours' copies of the same vector (NVLink stores), fences, and the last CTA to
+//    get there raises the neighbours' sequence flags;
+//  * a consumer reaching the first tile with halo columns waits (once) for the flags of the ranks it reads from.
+// The exchange therefore overlaps the interior rows, there is no separate push / wait launch and no copy: the
+// peers write straight into the tail of x, which starts on a fresh 128-byte line (HALO_ALIGN) so no L1 line
+// fetched for owned entries can hold stale halo entries.  x is not __restrict__/read-only in this instantiation:
+// its tail changes while the kernel runs.
+template <bool HALO> struct XArg { typedef const double *__restrict__ type; };   // read-only for the whole kernel
+template <> struct XArg<true> { typedef const double *type; };                      // its halo tail is written by peers
+
+template <bool DOT, bool HALO>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 k_spmv_tile3(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
-             const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, BulkLayout L,
-             double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar) {
+             const double *__restrict__ vals, typename XArg<HALO>::type x, double *__restrict__ y, BulkLayout L,
+             double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar, HaloArgs ha) {
     if (st && st->done) return;
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ __align__(8) uint64_t s_full[T3_GROUPS], s_empty[T3_GROUPS];
     __shared__ double s_part[T3_GROUPS][T3_PARTS][3 * T3_ROWS];
+#define X_AT(i) x[i]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nchunks = (nrows + T3_ROWS - 1) / T3_ROWS;
     const int64_t my_n = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned long long expect = HALO ? st->halo_seq + 1 : 0;     // every CTA reads it before any CTA can finish
     if (tid == 0) {
         for (int i = 0; i < T3_GROUPS; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], T3_GW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    auto tile_of = [&](int64_t i) -> int64_t {             // i-th tile of this CTA
+        const int64_t g = blockIdx.x + i * (int64_t)gridDim.x;
+        return HALO ? (int64_t)ha.tile_order[g] : g;
+    };
 
     double dsum = 0.0;
     if (warp == T3_GROUPS * T3_GW) {
-        if (lane == 0) {                                   // ---- producer ----
-            for (int64_t i = 0; i < my_n; i++) {
-                const int g = (int)(i % T3_GROUPS);
-                const int64_t k = i / T3_GROUPS;
-                if (k > 0) mbar_wait(&s_empty[g], (uint32_t)((k - 1) & 1));
-                const int64_t r0 = (blockIdx.x + i * (int64_t)gridDim.x) * T3_ROWS;
-                const int64_t r1 = (r0 + T3_ROWS < nrows) ? r0 + T3_ROWS : nrows;
-                unsigned char *base = s_raw + (size_t)g * L.stage_bytes;
-                const int64_t b0 = brow_ptr[r0], b1 = brow_ptr[r1];
-                const int64_t voff = 72 * b0, voff_al = voff & ~(int64_t)15;
-                const uint32_t vbytes = (uint32_t)(((voff - voff_al) + 72 * (b1 - b0) + 15) & ~(int64_t)15);
-                const int64_t coff = 4 * b0, coff_al = coff & ~(int64_t)15;
-                const uint32_t cbytes = (uint32_t)(((coff - coff_al) + 4 * (b1 - b0) + 15) & ~(int64_t)15);
-                const uint32_t rbytes = (uint32_t)((4 * (r1 - r0 + 1) + 15) & ~(int64_t)15);
-                mbar_expect_tx(&s_full[g], vbytes + cbytes + rbytes);
-                bulk_g2s(base + L.vals_off, (const unsigned char *)vals + voff_al, vbytes, &s_full[g]);
-                bulk_g2s(base + L.cols_off, (const unsigned char *)bcol + coff_al, cbytes, &s_full[g]);
-                bulk_g2s(base + L.rp_off, (const unsigned char *)(brow_ptr + r0), rbytes, &s_full[g]);
+        // ---- producer ----
+        auto issue = [&](int64_t i) {                      // lane 0 only
+            const int g = (int)(i % T3_GROUPS);
+            const int64_t k = i / T3_GROUPS;
+            if (k > 0) mbar_wait(&s_empty[g], (uint32_t)((k - 1) & 1));
+            const int64_t r0 = tile_of(i) * T3_ROWS;
+            const int64_t r1 = (r0 + T3_ROWS < nrows) ? r0 + T3_ROWS : nrows;
+            unsigned char *base = s_raw + (size_t)g * L.stage_bytes;
+            const int64_t b0 = brow_ptr[r0], b1 = brow_ptr[r1];
+            const int64_t voff = 72 * b0, voff_al = voff & ~(int64_t)15;
+            const uint32_t vbytes = (uint32_t)(((voff - voff_al) + 72 * (b1 - b0) + 15) & ~(int64_t)15);
+            const int64_t coff = 4 * b0, coff_al = coff & ~(int64_t)15;
+            const uint32_t cbytes = (uint32_t)(((coff - coff_al) + 4 * (b1 - b0) + 15) & ~(int64_t)15);
+            const uint32_t rbytes = (uint32_t)((4 * (r1 - r0 + 1) + 15) & ~(int64_t)15);
+            mbar_expect_tx(&s_full[g], vbytes + cbytes + rbytes);
+            bulk_g2s(base + L.vals_off, (const unsigned char *)vals + voff_al, vbytes, &s_full[g]);
+            bulk_g2s(base + L.cols_off, (const unsigned char *)bcol + coff_al, cbytes, &s_full[g]);
+            bulk_g2s(base + L.rp_off, (const unsigned char *)(brow_ptr + r0), rbytes, &s_full[g]);
+        };
+        const int64_t first = my_n < T3_GROUPS ? my_n : T3_GROUPS;
+        if (lane == 0)
+            for (int64_t i = 0; i < first; i++) issue(i);
+        if (HALO) {                                        // the whole warp pushes while the consumers start
+            const CommDev *cd = ha.cd;
+            const int W = cd->world, me = cd->rank;
+            const long long n3 = 3 * cd->send_off[W];
+            int peer = 0;
+            for (long long t = blockIdx.x * 32ll + lane; t < n3; t += 32ll * gridDim.x) {
+                const long long i = t / 3;
+                while (i >= cd->send_off[peer + 1]) peer++;          // t only grows
+                cd->vec[peer][ha.vec_id][cd->tail_off[peer] + 3 * (i - cd->send_off[peer]) + (t - 3 * i)] =
+                    x[3 * (long long)cd->send_rows[i] + (t - 3 * i)];
+            }
+            __threadfence_system();
+            __syncwarp();
+            unsigned int ticket = 0;
+            if (lane == 0) ticket = atomicInc(cd->ticket, gridDim.x - 1);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            if (ticket == gridDim.x - 1 && lane < W && lane != me && cd->send_off[lane + 1] > cd->send_off[lane]) {
+                __threadfence_system();
+                *(volatile unsigned long long *)&cd->ctrl[lane]->hflag[me] = expect;
             }
         }
+        if (lane == 0)
+            for (int64_t i = first; i < my_n; i++) issue(i);
     } else {
         const int g = warp / T3_GW, wg = warp % T3_GW;     // ---- consumers ----
         const int part = wg / 3, t = (wg % 3) * 32 + lane; // scalar row of the tile
         const int br = t / 3, a = t - 3 * br;
         const unsigned char *base = s_raw + (size_t)g * L.stage_bytes;
         const int32_t *rp = reinterpret_cast<const int32_t *>(base + L.rp_off);
+        bool halo_ready = !HALO;
         for (int64_t i = g, k = 0; i < my_n; i += T3_GROUPS, k++) {
+            if (HALO && !halo_ready && blockIdx.x + i * (int64_t)gridDim.x >= ha.n_interior) {
+                const CommDev *cd = ha.cd;                 // first tile with halo columns: wait for the neighbours
+                if (lane < cd->n_recv_peers) {
+                    const unsigned long long *f = &cd->ctrl[cd->rank]->hflag[cd->recv_peer[lane]];
+                    const long long t0 = clock64();
+                    unsigned long long seen;
+                    do {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+                        if (clock64() - t0 > 8000000000LL) { atomicOr(cd->err + 4, 1); break; }   // ~4 s: a peer died
+                    } while (seen < expect);
+                }
+                __syncwarp();
+                halo_ready = true;
+            }
             mbar_wait(&s_full[g], (uint32_t)(k & 1));
-            const int64_t r0 = (blockIdx.x + i * (int64_t)gridDim.x) * T3_ROWS;
+            const int64_t r0 = tile_of(i) * T3_ROWS;
             const int nr = (int)((nrows - r0) < T3_ROWS ? (nrows - r0) : T3_ROWS);
             double acc = 0.0;
             if (br < nr) {
@@ -585,10 +674,10 @@ k_spmv_tile3(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t 
                 double acc1 = 0.0, acc2 = 0.0;
 #pragma unroll 3
                 for (int c = c0; c < c1; c++) {
-                    const double *xp = x + 3 * (int64_t)cols[c];
-                    acc += v[3 * c] * xp[0];
-                    acc1 += v[3 * c + 1] * xp[1];
-                    acc2 += v[3 * c + 2] * xp[2];
+                    const int64_t xo = 3 * (int64_t)cols[c];
+                    acc += v[3 * c] * X_AT(xo);
+                    acc1 += v[3 * c + 1] * X_AT(xo + 1);
+                    acc2 += v[3 * c + 2] * X_AT(xo + 2);
                 }
                 acc = (acc + acc1) + acc2;
             }
@@ -598,15 +687,17 @@ k_spmv_tile3(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t 
                 const double sum = (s_part[g][0][t] + s_part[g][1][t]) + s_part[g][2][t];
                 const int64_t dof = 3 * (r0 + br) + a;
                 y[dof] = sum;
-                if (DOT) dsum += sum * x[dof];
+                if (DOT) dsum += sum * X_AT(dof);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[g]);
         }
     }
+#undef X_AT
     if (DOT) {
         double v[1] = {dsum};
-        grid_reduce<1>(v, partials, counter, st, slot, step, run_scalar);
+        const bool last = grid_reduce<1>(v, partials, counter, st, slot, step, run_scalar);
+        if (HALO && last && tid == 0) st->halo_seq = expect;          // this exchange is complete on this rank
     }
 }
 
@@ -767,8 +858,9 @@ static int spmv_plan(const stan_handle *h, int64_t nrows, SpmvPlan *p) {
         p->smem = (size_t)T3_GROUPS * p->L.stage_bytes;
         if (p->smem > 215 * 1024) p->variant = 0;
         else {
-            STAN_CUDA(cudaFuncSetAttribute(k_spmv_tile3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-            STAN_CUDA(cudaFuncSetAttribute(k_spmv_tile3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+            STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
+            STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
+            STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
             const int64_t nchunks = (nrows + T3_ROWS - 1) / T3_ROWS;
             p->grid = (int)(nchunks < h->sm_count ? (nchunks > 0 ? nchunks : 1) : h->sm_count);
             return STAN_OK;
@@ -813,19 +905,24 @@ static int spmv_plan(const stan_handle *h, int64_t nrows, SpmvPlan *p) {
     return STAN_OK;
 }
 
+// ha != nullptr: the product exchanges the halo of `in` itself (variant 4, peer-memory mode, inside a solve)
 static void launch_spmv(const stan_handle *h, const SpmvPlan &p, bool dot, int64_t nrows, const double *in, double *out,
                         double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar,
-                        cudaStream_t s) {
+                        cudaStream_t s, const HaloArgs *ha = nullptr) {
 #define STAN_LAUNCH_TILE(D, R, G)                                                                                  \
     k_spmv_tile<D, R, G><<<p.grid, 32 * (G * ((3 * R + 31) / 32) + 1), p.smem, s>>>(                               \
         nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out, p.L, partials, counter, st, slot, step, run_scalar)
     if (p.variant == 4) {
-        if (dot)
-            k_spmv_tile3<true><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out, p.L,
-                                                                  partials, counter, st, slot, step, run_scalar);
+        const HaloArgs none = {nullptr, nullptr, 0, 0};
+        if (ha)
+            k_spmv_tile3<true, true><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
+                                                                        p.L, partials, counter, st, slot, step, run_scalar, *ha);
+        else if (dot)
+            k_spmv_tile3<true, false><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
+                                                                         p.L, partials, counter, st, slot, step, run_scalar, none);
         else
-            k_spmv_tile3<false><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out, p.L,
-                                                                   partials, counter, st, slot, step, run_scalar);
+            k_spmv_tile3<false, false><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
+                                                                          p.L, partials, counter, st, slot, step, run_scalar, none);
         return;
     }
     if (p.variant == 2) { if (dot) STAN_LAUNCH_TILE(true, 16, 6); else STAN_LAUNCH_TILE(false, 16, 6); return; }
@@ -851,7 +948,7 @@ static void launch_spmv(const stan_handle *h, const SpmvPlan &p, bool dot, int64
 
 int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     cudaStream_t s = h->stream;
-    const int64_t nloc = h->row1 - h->row0, n = 3 * nloc, nx = 3 * (nloc + h->n_halo);
+    const int64_t nloc = h->row1 - h->row0, n = 3 * nloc, nx = 3 * (h->nloc_pad + h->n_halo);
     const bool multi = h->world > 1;
     const bool p2p = multi && comm_p2p_active(h);
     const bool single = !multi || p2p;      // reductions finish inside the producing kernel
@@ -862,8 +959,10 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     const int64_t restart = o->its_before_restart > 0 ? o->its_before_restart : (n_global_free > 0 ? n_global_free : 1);
     const int off = o->zero_based_counter ? 1 : 0;
 
-    STAN_TRY(h->d_x.alloc(nx, s)); STAN_TRY(h->d_xalt.alloc(nx, s));
-    STAN_TRY(h->d_r.alloc(n, s)); STAN_TRY(h->d_p.alloc(nx, s)); STAN_TRY(h->d_mv.alloc(n, s));
+    // the vectors a product reads (p, x, xalt): [owned | pad | halo]; in peer-memory mode they live in the window
+    double *vp = nullptr, *vx = nullptr, *vxalt = nullptr;
+    STAN_TRY(comm_cg_vectors(h, &vp, &vx, &vxalt, s));
+    STAN_TRY(h->d_r.alloc(n, s)); STAN_TRY(h->d_mv.alloc(n, s));
     SpmvPlan plan;
     STAN_TRY(spmv_plan(h, nloc, &plan));
     const int gv = vec_grid(h, n), gs = plan.grid;
@@ -872,9 +971,10 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     STAN_TRY(h->d_state.alloc(1, s));
     STAN_TRY(h->d_counter.alloc(4, s));
     STAN_CUDA(cudaMemsetAsync(h->d_counter.p, 0, 4 * sizeof(unsigned int), s));
-    if (h->n_halo) {
-        STAN_CUDA(cudaMemsetAsync(h->d_p.p + n, 0, (nx - n) * sizeof(double), s));
-        STAN_CUDA(cudaMemsetAsync(h->d_xalt.p + n, 0, (nx - n) * sizeof(double), s));
+    if (h->n_halo && !p2p) {                 // (peer-memory mode: the tails belong to the peers, nothing to clear)
+        STAN_CUDA(cudaMemsetAsync(vp + n, 0, (nx - n) * sizeof(double), s));
+        STAN_CUDA(cudaMemsetAsync(vx + n, 0, (nx - n) * sizeof(double), s));
+        STAN_CUDA(cudaMemsetAsync(vxalt + n, 0, (nx - n) * sizeof(double), s));
     }
     CgState init;
     memset(&init, 0, sizeof init);
@@ -883,6 +983,7 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     init.restart = restart;
     init.comm = p2p ? comm_dev(h) : nullptr;
     init.red_seq = h->red_seq;              // flags in the peer windows persist across solves
+    init.halo_seq = p2p ? comm_next_epoch(h) << 32 : 0;   // a new epoch: flags of earlier solves can never satisfy a wait
     if (h->hist_cap > 0) {
         STAN_TRY(h->d_hist.alloc((size_t)4 * h->hist_cap, s));
         init.hist = h->d_hist.p;
@@ -893,7 +994,8 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     *hst = init;
     STAN_CUDA(cudaMemcpyAsync(h->d_state.p, hst, sizeof(CgState), cudaMemcpyHostToDevice, s));
     CgState *st = h->d_state.p;
-    double *x = h->d_x.p, *xalt = h->d_xalt.p;
+    double *x = vx, *xalt = vxalt;
+    const bool fused_halo = p2p && plan.variant == 4;      // the product kernel exchanges its own halo
     int64_t launches = 0;
     int spmv_launches = 0;
     float spmv_ms = 0.f;
@@ -910,7 +1012,10 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
         return STAN_OK;
     };
     auto spmv = [&](double *in, int slot, int step) -> int {
-        if (multi) STAN_TRY(comm_halo_exchange(h, in, s, st));
+        const int vec_id = in == vp ? 0 : (in == vx ? 1 : 2);
+        HaloArgs ha;
+        const bool fuse = fused_halo && comm_halo_args(h, vec_id, &ha);
+        if (multi && !fuse) STAN_TRY(comm_halo_exchange(h, in, vec_id, s, st));
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (timek) {                                       // events come from a grow-only pool kept on the handle
             if (h->ev_pool.size() < evs.size() + 2) {
@@ -920,14 +1025,15 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
             e0 = h->ev_pool[evs.size()]; e1 = h->ev_pool[evs.size() + 1];
             cudaEventRecord(e0, s);
         }
-        launch_spmv(h, plan, true, nloc, in, h->d_mv.p, h->d_partials.p, h->d_counter.p + 2, st, slot, step, single, s);
+        launch_spmv(h, plan, true, nloc, in, h->d_mv.p, h->d_partials.p, h->d_counter.p + 2, st, slot, step, single, s,
+                    fuse ? &ha : nullptr);
         if (timek) { cudaEventRecord(e1, s); evs.push_back(e0); evs.push_back(e1); }
         launches++; spmv_launches++;
         if (step != SC_NONE) STAN_TRY(reduce_tail(step));
         return STAN_OK;
     };
 
-    k_cg_init<<<gv, VEC_THREADS, 0, s>>>(n, h->d_b.p, h->d_d2.p, x, h->d_r.p, h->d_p.p, h->d_partials.p,
+    k_cg_init<<<gv, VEC_THREADS, 0, s>>>(n, h->d_b.p, h->d_d2.p, x, h->d_r.p, vp, h->d_partials.p,
                                          h->d_counter.p, st, single);
     launches++;
     STAN_TRY(reduce_tail(SC_INIT));
@@ -944,14 +1050,14 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
             k++;
             const int kk = k - off;
             const bool refresh = rupd > 0 && kk % rupd == 0;
-            STAN_TRY(spmv(h->d_p.p, 0, SC_AFTER_SPMV));
+            STAN_TRY(spmv(vp, 0, SC_AFTER_SPMV));
             if (!refresh) {
                 k_update<<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_mv.p, h->d_d2.p, h->d_partials.p, h->d_counter.p, st,
                                                     single);
                 launches++;
                 STAN_TRY(reduce_tail(SC_AFTER_UPDATE));
             } else {
-                k_candidate<<<gv, VEC_THREADS, 0, s>>>(n, x, h->d_p.p, xalt, st);
+                k_candidate<<<gv, VEC_THREADS, 0, s>>>(n, x, vp, xalt, st);
                 launches++;
                 STAN_TRY(spmv(xalt, 3, SC_NONE));
                 k_refresh<<<gv, VEC_THREADS, 0, s>>>(n, h->d_b.p, h->d_mv.p, xalt, h->d_d2.p, h->d_r.p,
@@ -960,8 +1066,8 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
                 STAN_TRY(reduce_tail(SC_AFTER_REFRESH));
                 double *t = x; x = xalt; xalt = t;         // accepted unless the state says type 7
             }
-            if (refresh) k_direction<false><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, h->d_p.p, x, st);
-            else         k_direction<true><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, h->d_p.p, x, st);
+            if (refresh) k_direction<false><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, vp, x, st);
+            else         k_direction<true><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, vp, x, st);
             launches++;
         }
         return STAN_OK;
@@ -1002,7 +1108,7 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
     if (hst->x_pending) {
-        k_x_tail<<<gv, VEC_THREADS, 0, s>>>(n, h->d_x.p, h->d_xalt.p, h->d_p.p, st);
+        k_x_tail<<<gv, VEC_THREADS, 0, s>>>(n, vx, vxalt, vp, st);
         launches++;
     }
     STAN_CUDA(cudaEventRecord(h->ev1, s));
@@ -1017,6 +1123,7 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     }
     // accepted iterate: d_x unless an odd number of refreshes were accepted
     h->x_in_alt = hst->x_in_alt != 0;
+    h->sol = h->x_in_alt ? vxalt : vx;
     h->red_seq = hst->red_seq;
     h->hist_count = hst->k < h->hist_cap ? hst->k : h->hist_cap;
     rep->terminationtype = hst->type;
@@ -1060,7 +1167,7 @@ int spmv_full(stan_handle *h, const double *x_full, double *y_full) {
 
 int time_spmv(stan_handle *h, int reps, double *ms_out, int64_t *bytes) {
     cudaStream_t s = h->stream;
-    const int64_t nloc = h->row1 - h->row0, nx = 3 * (nloc + h->n_halo);
+    const int64_t nloc = h->row1 - h->row0, nx = 3 * (h->nloc_pad + h->n_halo);
     DevBuf<double> x, y;
     STAN_TRY(x.alloc(nx, s)); STAN_TRY(y.alloc(3 * nloc, s));
     STAN_CUDA(cudaMemsetAsync(x.p, 0, nx * sizeof(double), s));
@@ -1087,7 +1194,7 @@ int scatter_solution(stan_handle *h) {
     cudaStream_t s = h->stream;
     const int64_t nloc = h->row1 - h->row0;
     STAN_TRY(h->d_ufull.alloc(3 * h->n_nodes, s));
-    const double *x = h->x_in_alt ? h->d_xalt.p : h->d_x.p;
+    const double *x = h->sol;
     if (h->world == 1) {
         STAN_CUDA(cudaMemcpyAsync(h->d_ufull.p, x, 3 * nloc * sizeof(double), cudaMemcpyDeviceToDevice, s));
     } else {

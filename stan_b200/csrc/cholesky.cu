@@ -483,6 +483,7 @@ int solve_cholesky(stan_handle *h, stan_chol_report *rep) {
     cudaEventElapsedTime(&t23, h->ev2, h->ev3);
     free_all();
     h->x_in_alt = false;
+    h->sol = h->d_x.p;
     h->solved = true;
     h->launches += launches;
     rep->terminationtype = spd ? 1 : -3;

@@ -7,6 +7,13 @@
 // its neighbours' boundary rows reference and receives its own halo; CG dot products are one
 // small all-reduce each.  Because adjacency is symmetric, a rank derives both its halo list and
 // its send lists from its own block columns — no set-up communication is needed.
+//
+// Default data plane (peer memory over NVLink, no library call in the CG loop): the three vectors an
+// SpMV reads live in a cudaMalloc'ed window that every peer maps through CUDA IPC.  The product kernel
+// itself stores its boundary entries into the halo tails of the neighbours' copies of that vector while
+// its consumer warps work through the tiles that need no halo, raises a sequence flag, and only the
+// tiles with halo columns wait for the neighbours' flags (cg.cu: k_spmv_tile3<.., true>).  NCCL is used
+// for set-up, and as the whole data plane with STAN_COMM=nccl or when IPC is unavailable.
 #include <cub/device/device_scan.cuh>
 #include <dlfcn.h>
 
@@ -65,8 +72,12 @@ struct Comm {
     nccl_comm comm = nullptr;
     // ---- peer-memory path ----
     bool p2p = false, p2p_failed = false;
-    void *window = nullptr;                // this rank's cudaMalloc'ed window (P2PCtrl + landing zones)
+    void *window = nullptr;                // this rank's cudaMalloc'ed window (P2PCtrl + the vectors p, x, xalt)
     size_t window_bytes = 0;
+    size_t vec_stride = 0;                 // doubles between the window vectors
+    unsigned long long epoch = 0;          // solves so far: high half of every halo sequence number
+    DevBuf<int32_t> d_tile_order;          // SpMV tiles, the ones without halo columns first
+    int64_t n_interior = 0;
     void *peer_window[P2P_MAX_RANKS] = {};   // IPC mappings of the other ranks' windows
     DevBuf<CommDev> d_dev;
     DevBuf<unsigned int> d_ticket;
@@ -119,6 +130,7 @@ void comm_destroy(stan_handle *h) {
     h->comm->d_send_rows.release(h->stream);
     h->comm->d_sendbuf.release(h->stream);
     h->comm->d_gather.release(h->stream);
+    h->comm->d_tile_order.release(h->stream);
     delete h->comm;
     h->comm = nullptr;
 }
@@ -140,11 +152,11 @@ __global__ void k_mark_halo(int64_t nblk, const int32_t *__restrict__ bcol, int6
 }
 
 __global__ void k_localize_cols(int64_t nblk, const int32_t *__restrict__ bcol, int64_t row0, int64_t row1,
-                                const int32_t *__restrict__ slot, int32_t *__restrict__ out) {
+                                int64_t halo_base, const int32_t *__restrict__ slot, int32_t *__restrict__ out) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t >= nblk) return;
     int32_t q = bcol[t];
-    out[t] = (q >= row0 && q < row1) ? (int32_t)(q - row0) : (int32_t)(row1 - row0) + slot[q];
+    out[t] = (q >= row0 && q < row1) ? (int32_t)(q - row0) : (int32_t)halo_base + slot[q];
 }
 
 // bit s of mask[row] is set when the row has a column owned by rank s
@@ -164,51 +176,52 @@ __global__ void k_peer_mask(int64_t nloc, const int32_t *__restrict__ brow_ptr, 
     mask[p] = m;
 }
 
-// Halo push: my boundary rows go straight into the landing zones of the ranks that read them.
-// The last CTA to finish raises the arrival flags (sequence number) after a system-scope fence.
+// Stand-alone halo exchange for the SpMV variants that do not push/wait themselves (rows too wide for the
+// tile kernel): same protocol as the fused kernel.  Push: my boundary entries of window vector `vec_id` go
+// straight into the halo tails of the ranks that read them; the last CTA raises the sequence flags after a
+// system-scope fence.  Every CTA takes a ticket even when the state says done, so the counter stays consistent.
 __global__ void __launch_bounds__(256)
-k_halo_push(const CommDev *__restrict__ cd, const int32_t *__restrict__ rows, const double *__restrict__ vec,
-            unsigned long long seq, unsigned int *ticket, const CgState *st) {
-    if (st && st->done) return;
-    const int W = cd->world, me = cd->rank, par = (int)(seq & 1);
-    const long long n3 = 3 * cd->send_off[W];
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n3; t += (long long)gridDim.x * blockDim.x) {
-        const long long i = t / 3;
-        int peer = 0;
-        while (i >= cd->send_off[peer + 1]) peer++;
-        double *dst = cd->rbuf[peer] + par * cd->rbuf_stride[peer] + 3 * (cd->land_off[peer] + (i - cd->send_off[peer])) + (t - 3 * i);
-        *dst = vec[3 * (long long)rows[i] + (t - 3 * i)];
+k_halo_push(const CommDev *__restrict__ cd, const double *__restrict__ vec, int vec_id, const CgState *st) {
+    const bool skip = st->done != 0;
+    const unsigned long long seq = st->halo_seq + 1;
+    const int W = cd->world, me = cd->rank;
+    if (!skip) {
+        const long long n3 = 3 * cd->send_off[W];
+        for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n3; t += (long long)gridDim.x * blockDim.x) {
+            const long long i = t / 3;
+            int peer = 0;
+            while (i >= cd->send_off[peer + 1]) peer++;
+            cd->vec[peer][vec_id][cd->tail_off[peer] + 3 * (i - cd->send_off[peer]) + (t - 3 * i)] =
+                vec[3 * (long long)cd->send_rows[i] + (t - 3 * i)];
+        }
+        __threadfence_system();
     }
-    __threadfence_system();
     __shared__ bool last;
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+    if (threadIdx.x == 0) last = (atomicInc(cd->ticket, gridDim.x - 1) == gridDim.x - 1);
     __syncthreads();
-    if (last && threadIdx.x < W && threadIdx.x != me && cd->send_off[threadIdx.x + 1] > cd->send_off[threadIdx.x]) {
+    if (last && !skip && threadIdx.x < W && threadIdx.x != me && cd->send_off[threadIdx.x + 1] > cd->send_off[threadIdx.x]) {
         __threadfence_system();
-        *(volatile unsigned long long *)&cd->ctrl[threadIdx.x]->hflag[par][me] = seq;
+        *(volatile unsigned long long *)&cd->ctrl[threadIdx.x]->hflag[me] = seq;
     }
 }
 
-// Halo wait: spin until every source rank has raised its flag for this exchange, then move the
-// landing zone (read through L2: the lines were written by a peer) behind the owned entries of vec.
-__global__ void __launch_bounds__(256)
-k_halo_wait(const CommDev *__restrict__ cd, double *__restrict__ vec, long long nloc3, long long nhalo3,
-            unsigned long long seq, CgState *st) {
-    if (st && st->done) return;
-    const int W = cd->world, me = cd->rank, par = (int)(seq & 1);
-    if (threadIdx.x < W && threadIdx.x != me && cd->recv_cnt[threadIdx.x] > 0) {
-        volatile unsigned long long *f = &cd->ctrl[me]->hflag[par][threadIdx.x];
+// Halo wait: spin until every source rank has raised its flag for this exchange; the entries are already in
+// the tail of the vector.  One CTA; it also advances the exchange counter of the solve.
+__global__ void __launch_bounds__(32)
+k_halo_wait(const CommDev *__restrict__ cd, CgState *st) {
+    if (st->done) return;
+    const unsigned long long seq = st->halo_seq + 1;
+    if ((int)threadIdx.x < cd->n_recv_peers) {
+        volatile unsigned long long *f = &cd->ctrl[cd->rank]->hflag[cd->recv_peer[threadIdx.x]];
         const long long t0 = clock64();
         while (*f < seq) {
             if (clock64() - t0 > 8000000000LL) { atomicOr(cd->err + 4, 1); break; }   // ~4 s: a peer died
         }
         __threadfence_system();
     }
-    __syncthreads();
-    const double *src = cd->rbuf[me] + par * cd->rbuf_stride[me];
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nhalo3; t += (long long)gridDim.x * blockDim.x)
-        vec[nloc3 + t] = __ldcg(src + t);
+    __syncwarp();
+    if (threadIdx.x == 0) st->halo_seq = seq;
 }
 
 __global__ void k_pack(int64_t n_send, const int32_t *__restrict__ rows, const double *__restrict__ vec,
@@ -228,6 +241,8 @@ void partition_rows(stan_handle *h) {
 // Peer-memory set-up: allocate this rank's window, swap IPC handles and landing offsets with an
 // NCCL all-gather (set-up only), map every peer window.  Falls back to the NCCL path when IPC is
 // unavailable or STAN_COMM=nccl.
+static size_t window_ctrl_bytes() { return (sizeof(P2PCtrl) + 255) & ~(size_t)255; }
+
 static int p2p_setup(stan_handle *h) {
     Comm *c = h->comm;
     cudaStream_t s = h->stream;
@@ -236,13 +251,16 @@ static int p2p_setup(stan_handle *h) {
     if ((mode && !strcmp(mode, "nccl")) || W > P2P_MAX_RANKS || c->p2p_failed) return STAN_OK;
 
     // phase 1: sizes and landing offsets (also a barrier: every rank has left its previous solve)
-    struct Hello { long long n_halo, need, cap; long long recv_off[P2P_MAX_RANKS]; };
-    struct Hello2 { cudaIpcMemHandle_t handle; int ok, pad; };
-    const size_t ctrl_bytes = (sizeof(P2PCtrl) + 255) & ~(size_t)255;
+    struct Hello { long long nloc_pad, n_halo, need, cap; long long recv_off[P2P_MAX_RANKS]; };
+    struct Hello2 { cudaIpcMemHandle_t handle; long long vec_stride; int ok, pad; };
+    const size_t ctrl_bytes = window_ctrl_bytes();
+    // one vector: owned rows padded, then the halo rows; rounded so the next vector starts on a 256-byte boundary
+    const size_t vec_doubles = ((size_t)3 * (h->nloc_pad + std::max<int64_t>(h->n_halo, 1)) + 31) & ~(size_t)31;
     Hello mine;
     memset(&mine, 0, sizeof mine);
+    mine.nloc_pad = h->nloc_pad;
     mine.n_halo = h->n_halo;
-    mine.need = (long long)(ctrl_bytes + 2 * (size_t)(3 * std::max<int64_t>(h->n_halo, 1)) * sizeof(double));
+    mine.need = (long long)(ctrl_bytes + 3 * vec_doubles * sizeof(double));
     mine.cap = c->window ? (long long)c->window_bytes : 0;
     for (int r = 0; r < W; r++) mine.recv_off[r] = c->recv_off[r];
     std::vector<Hello> all(W);
@@ -255,23 +273,25 @@ static int p2p_setup(stan_handle *h) {
         STAN_CUDA(cudaStreamSynchronize(s));
         dmine.release(s); dall.release(s);
     }
-    bool any_grow = false;
-    for (int r = 0; r < W; r++) any_grow = any_grow || all[r].need > all[r].cap;
+    const bool grow = mine.need > mine.cap;
 
-    // phase 2 (only when some window must grow): new allocations, new IPC handles, new mappings
-    if (any_grow) {
-        Hello2 m2;
-        memset(&m2, 0, sizeof m2);
-        m2.ok = 1;
-        if (all[me].need > all[me].cap) {
-            if (c->window) { cudaFree(c->window); c->window = nullptr; }
-            c->window_bytes = std::max<size_t>((size_t)all[me].need * 2, (size_t)1 << 20);
-            m2.ok = cudaMalloc(&c->window, c->window_bytes) == cudaSuccess;
-            if (m2.ok) cudaMemset(c->window, 0, c->window_bytes);
-        }
-        if (m2.ok) m2.ok = cudaIpcGetMemHandle(&m2.handle, c->window) == cudaSuccess;
-        cudaGetLastError();
-        std::vector<Hello2> all2(W);
+    // phase 2: (new) allocations, IPC handles, vector strides; windows that did not grow keep their mapping
+    Hello2 m2;
+    memset(&m2, 0, sizeof m2);
+    m2.ok = 1;
+    if (grow) {
+        if (c->window) { cudaFree(c->window); c->window = nullptr; }
+        c->window_bytes = (size_t)mine.need + (size_t)mine.need / 8;
+        m2.ok = cudaMalloc(&c->window, c->window_bytes) == cudaSuccess;
+        if (m2.ok) cudaMemset(c->window, 0, c->window_bytes);
+    }
+    // the vectors are re-laid inside the (possibly larger) window for this model's size
+    c->vec_stride = vec_doubles;
+    m2.vec_stride = (long long)vec_doubles;
+    if (m2.ok) m2.ok = cudaIpcGetMemHandle(&m2.handle, c->window) == cudaSuccess;
+    cudaGetLastError();
+    std::vector<Hello2> all2(W);
+    {
         ScratchBuf<Hello2> dmine(&h->scratch[4]), dall(&h->scratch[5]);
         STAN_TRY(dmine.alloc(1, s)); STAN_TRY(dall.alloc(W, s));
         STAN_CUDA(cudaMemcpyAsync(dmine.p, &m2, sizeof m2, cudaMemcpyHostToDevice, s));
@@ -279,15 +299,16 @@ static int p2p_setup(stan_handle *h) {
         STAN_CUDA(cudaMemcpyAsync(all2.data(), dall.p, W * sizeof(Hello2), cudaMemcpyDeviceToHost, s));
         STAN_CUDA(cudaStreamSynchronize(s));
         dmine.release(s); dall.release(s);
-        bool ok = true;
-        for (int r = 0; r < W; r++) ok = ok && all2[r].ok;
-        for (int r = 0; r < W && ok; r++) {
-            if (r == me || !(all[r].need > all[r].cap)) continue;       // unchanged windows keep their mapping
-            if (c->peer_window[r]) { cudaIpcCloseMemHandle(c->peer_window[r]); c->peer_window[r] = nullptr; }
-            if (cudaIpcOpenMemHandle(&c->peer_window[r], all2[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
-        }
-        cudaGetLastError();
-        // every rank must take the same path: agree on success
+    }
+    bool ok = true;
+    for (int r = 0; r < W; r++) ok = ok && all2[r].ok;
+    for (int r = 0; r < W && ok; r++) {
+        if (r == me || !(all[r].need > all[r].cap)) continue;       // unchanged windows keep their mapping
+        if (c->peer_window[r]) { cudaIpcCloseMemHandle(c->peer_window[r]); c->peer_window[r] = nullptr; }
+        if (cudaIpcOpenMemHandle(&c->peer_window[r], all2[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = false;
+    }
+    cudaGetLastError();
+    {   // every rank must take the same path: agree on success
         double flag = ok ? 0.0 : 1.0;
         DevBuf<double> dflag;
         STAN_TRY(dflag.alloc(1, s));
@@ -302,20 +323,22 @@ static int p2p_setup(stan_handle *h) {
     memset(&dev, 0, sizeof dev);
     dev.rank = me; dev.world = W; dev.err = h->d_err.p;
     for (int r = 0; r < W; r++) {
-        void *base = r == me ? c->window : c->peer_window[r];
+        char *base = (char *)(r == me ? c->window : c->peer_window[r]);
         dev.ctrl[r] = (P2PCtrl *)base;
-        dev.rbuf[r] = (double *)((char *)base + ctrl_bytes);
-        dev.rbuf_stride[r] = 3 * std::max<long long>(all[r].n_halo, 1);
-        dev.land_off[r] = all[r].recv_off[me];
+        for (int v = 0; v < 3; v++) dev.vec[r][v] = (double *)(base + ctrl_bytes) + (size_t)v * all2[r].vec_stride;
+        dev.tail_off[r] = 3 * (all[r].nloc_pad + all[r].recv_off[me]);
         dev.recv_cnt[r] = c->recv_cnt[r];
         dev.send_off[r] = c->send_off[r];
+        if (r != me && c->recv_cnt[r] > 0) dev.recv_peer[dev.n_recv_peers++] = r;
     }
     dev.send_off[W] = c->n_send;
+    dev.send_rows = c->d_send_rows.p;
     STAN_TRY(c->d_dev.alloc(1, s));
     if (!c->d_ticket.p) {
         STAN_TRY(c->d_ticket.alloc(1, s));
         STAN_CUDA(cudaMemsetAsync(c->d_ticket.p, 0, sizeof(unsigned int), s));
     }
+    dev.ticket = c->d_ticket.p;
     STAN_CUDA(cudaMemcpyAsync(c->d_dev.p, &dev, sizeof dev, cudaMemcpyHostToDevice, s));
     STAN_CUDA(cudaStreamSynchronize(s));
     c->p2p = true;
@@ -326,10 +349,12 @@ int comm_build_halo(stan_handle *h) {
     cudaStream_t s = h->stream;
     const int64_t nloc = h->row1 - h->row0, nn = h->n_nodes;
     h->n_halo = 0;
+    h->nloc_pad = nloc;
     if (h->world <= 1) { h->bcol_x = h->d_bcol.p; return STAN_OK; }
     if (!h->comm || !h->comm->comm) { set_error("world > 1 but stan_comm_init was not called"); return STAN_E_STATE; }
     Comm *c = h->comm;
     const int W = h->world;
+    h->nloc_pad = (nloc + HALO_ALIGN - 1) / HALO_ALIGN * HALO_ALIGN;
     c->bound.resize(W + 1);
     for (int r = 0; r <= W; r++) c->bound[r] = nn * (int64_t)r / W;
     c->max_rows = 0;
@@ -347,8 +372,8 @@ int comm_build_halo(stan_handle *h) {
         STAN_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, flag.p, slot.p, nn + 1, s));
     }
     STAN_TRY(h->d_bcol_loc.alloc((size_t)h->n_blocks + 4, s));
-    k_localize_cols<<<div_up(h->n_blocks, 256), 256, 0, s>>>(h->n_blocks, h->d_bcol.p, h->row0, h->row1, slot.p,
-                                                             h->d_bcol_loc.p);
+    k_localize_cols<<<div_up(h->n_blocks, 256), 256, 0, s>>>(h->n_blocks, h->d_bcol.p, h->row0, h->row1, h->nloc_pad,
+                                                             slot.p, h->d_bcol_loc.p);
     h->bcol_x = h->d_bcol_loc.p;
     // halo segment of every owner = difference of the scan at its bounds
     std::vector<int32_t> at(W + 1);
@@ -382,22 +407,60 @@ int comm_build_halo(stan_handle *h) {
     STAN_TRY(c->d_sendbuf.alloc(3 * rows.size(), s));
     if (!rows.empty())
         STAN_CUDA(cudaMemcpyAsync(c->d_send_rows.p, rows.data(), rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    // SpMV tile order (32-row tiles, cg.cu): the tiles whose rows have no halo column first, so the product can
+    // start on them while the halo is still in flight; a row has a halo column iff its peer mask is non-zero
+    {
+        const int64_t n_tiles = (nloc + 31) / 32;
+        std::vector<int32_t> order((size_t)n_tiles);
+        int64_t w = 0;
+        std::vector<uint8_t> boundary((size_t)n_tiles, 0);
+        for (int64_t p = 0; p < nloc; p++)
+            if (hmask[p]) boundary[p >> 5] = 1;
+        for (int64_t t = 0; t < n_tiles; t++) if (!boundary[t]) order[w++] = (int32_t)t;
+        c->n_interior = w;
+        for (int64_t t = 0; t < n_tiles; t++) if (boundary[t]) order[w++] = (int32_t)t;
+        STAN_TRY(c->d_tile_order.alloc((size_t)n_tiles, s));
+        STAN_CUDA(cudaMemcpyAsync(c->d_tile_order.p, order.data(), n_tiles * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    }
     STAN_CUDA(cudaStreamSynchronize(s));
     h->launches += 4;
     return p2p_setup(h);
 }
 
-// vec holds 3*nloc owned entries followed by 3*n_halo halo entries
-int comm_halo_exchange(stan_handle *h, double *d_vec, cudaStream_t s, CgState *st) {
+// The vectors an SpMV is applied to: inside the peer window in peer-memory mode, pool allocations otherwise.
+// Layout [3*nloc owned | pad | 3*n_halo halo] with the tail starting at 3*nloc_pad.
+int comm_cg_vectors(stan_handle *h, double **p, double **x, double **xalt, cudaStream_t s) {
+    const size_t nx = (size_t)3 * (h->nloc_pad + h->n_halo);
+    if (comm_p2p_active(h)) {
+        Comm *c = h->comm;
+        double *base = (double *)((char *)c->window + window_ctrl_bytes());
+        *p = base; *x = base + c->vec_stride; *xalt = base + 2 * c->vec_stride;
+        return STAN_OK;
+    }
+    STAN_TRY(h->d_p.alloc(nx, s)); STAN_TRY(h->d_x.alloc(nx, s)); STAN_TRY(h->d_xalt.alloc(nx, s));
+    *p = h->d_p.p; *x = h->d_x.p; *xalt = h->d_xalt.p;
+    return STAN_OK;
+}
+
+bool comm_halo_args(const stan_handle *h, int vec_id, HaloArgs *out) {
+    if (!comm_p2p_active(h)) return false;
+    out->cd = h->comm->d_dev.p;
+    out->tile_order = h->comm->d_tile_order.p;
+    out->n_interior = h->comm->n_interior;
+    out->vec_id = vec_id;
+    return true;
+}
+
+unsigned long long comm_next_epoch(stan_handle *h) { return h->comm ? ++h->comm->epoch : 0; }
+
+// vec holds 3*nloc owned entries, padding, and 3*n_halo halo entries from 3*nloc_pad on
+int comm_halo_exchange(stan_handle *h, double *d_vec, int vec_id, cudaStream_t s, CgState *st) {
     if (h->world <= 1) return STAN_OK;
     Comm *c = h->comm;
-    const int64_t nloc = h->row1 - h->row0;
     if (c->p2p) {
-        const unsigned long long seq = ++c->halo_seq;
         const int gp = (int)std::min<int64_t>(std::max<int64_t>(div_up(3 * c->n_send, 256), 1), 64);
-        k_halo_push<<<gp, 256, 0, s>>>(c->d_dev.p, c->d_send_rows.p, d_vec, seq, c->d_ticket.p, st);
-        const int gw = (int)std::min<int64_t>(std::max<int64_t>(div_up(3 * h->n_halo, 256), 1), 64);
-        k_halo_wait<<<gw, 256, 0, s>>>(c->d_dev.p, d_vec, 3 * nloc, 3 * h->n_halo, seq, st);
+        k_halo_push<<<gp, 256, 0, s>>>(c->d_dev.p, d_vec, vec_id, st);
+        k_halo_wait<<<1, 32, 0, s>>>(c->d_dev.p, st);
         h->launches += 2;
         return STAN_OK;
     }
@@ -411,7 +474,7 @@ int comm_halo_exchange(stan_handle *h, double *d_vec, cudaStream_t s, CgState *s
         if (c->send_cnt[r])
             STAN_NCCL(g_nccl.Send(c->d_sendbuf.p + 3 * c->send_off[r], (size_t)(3 * c->send_cnt[r]), NCCL_F64, r, c->comm, s));
         if (c->recv_cnt[r])
-            STAN_NCCL(g_nccl.Recv(d_vec + 3 * (nloc + c->recv_off[r]), (size_t)(3 * c->recv_cnt[r]), NCCL_F64, r, c->comm, s));
+            STAN_NCCL(g_nccl.Recv(d_vec + 3 * (h->nloc_pad + c->recv_off[r]), (size_t)(3 * c->recv_cnt[r]), NCCL_F64, r, c->comm, s));
     }
     STAN_NCCL(g_nccl.GroupEnd());
     return STAN_OK;

@@ -92,22 +92,36 @@ struct ScratchBuf {
 // Peer-memory window of one rank (multi-GPU, comm.cu).  Every rank cudaMalloc's one window, the
 // ranks exchange CUDA IPC handles once per assemble, and from then on halo values and partial sums
 // travel as plain stores into the neighbour's window over NVLink — no collective library in the CG
-// loop.  Control block first, halo landing zones (double-buffered by exchange parity) after it.
+// loop.  Control block first, then the three CG vectors an SpMV can be applied to (p, x, xalt), each
+// laid out as [owned rows padded to 16 nodes | halo rows]: a peer stores its boundary entries straight
+// into the halo tail of the vector the product will read — there is no landing zone and no copy.
 constexpr int P2P_MAX_RANKS = 32;
+constexpr int HALO_ALIGN = 16;                    // nodes: 16 * 3 * 8 B = 3 cache lines, so no 128-byte line
+                                                  // holds both owned entries and halo entries of a vector
 struct P2PCtrl {
-    unsigned long long hflag[2][P2P_MAX_RANKS];   // halo arrival: sequence number per source rank
-    unsigned long long rflag[2][P2P_MAX_RANKS];   // reduction arrival
-    double red[2][P2P_MAX_RANKS][4];              // partial sums per source rank
+    unsigned long long hflag[P2P_MAX_RANKS];      // halo arrival per source rank: (solve epoch << 32) | exchange count
+    unsigned long long red[2][P2P_MAX_RANKS][4][2];   // partial sums per source rank as two flag-carrying words each
 };
 struct CommDev {                                   // device-resident view used by kernels
     int rank, world;
+    int n_recv_peers;
+    int recv_peer[P2P_MAX_RANKS];                 // ranks that own halo rows of mine
     P2PCtrl *ctrl[P2P_MAX_RANKS];                 // ctrl[r]: window of rank r (own or IPC-mapped)
-    double *rbuf[P2P_MAX_RANKS];                  // rbuf[r]: landing zone of rank r, parity 0
-    long long rbuf_stride[P2P_MAX_RANKS];         // doubles between parity 0 and 1 of rank r
-    long long land_off[P2P_MAX_RANKS];            // where my rows start in rank r's landing zone (nodes)
+    double *vec[P2P_MAX_RANKS][3];                // the window vectors of rank r: 0 = p, 1 = x, 2 = xalt
+    long long tail_off[P2P_MAX_RANKS];            // doubles from the start of rank r's vectors to where my rows land
     long long send_off[P2P_MAX_RANKS + 1];        // my send list grouped by destination rank (nodes)
     long long recv_cnt[P2P_MAX_RANKS];            // halo nodes I receive from rank r
+    const int32_t *send_rows;                     // local row of every node to send, grouped by destination
+    unsigned int *ticket;                         // last-CTA detection of the push
     int *err;                                      // device error flags of the handle
+};
+
+// What the fused SpMV needs to exchange the halo of its input vector itself (cg.cu: k_spmv_tile3<.., true>).
+struct HaloArgs {
+    const CommDev *cd;
+    const int32_t *tile_order;                    // tiles without halo columns first
+    long long n_interior;                         // how many of them
+    int vec_id;                                   // which window vector the product reads
 };
 
 // Device-resident CG scalars: every decision ALGLIB's lincgiteration takes on the host is taken
@@ -130,6 +144,7 @@ struct CgState {
     int32_t x_pending;// 1 when the solve ended at an ordinary iteration whose x += alpha p is still owed
     CommDev *comm;    // peer-memory reductions (multi-GPU P2P mode), else nullptr
     unsigned long long red_seq;   // reductions published so far (same on every rank)
+    unsigned long long halo_seq;  // (solve epoch << 32) | halo exchanges completed in this solve (same on every rank)
     double *hist;     // stan_set_cg_history: rows k = 1.. of {||r_k||^2, alpha_k, beta_k, merit or NaN}, else nullptr
     int32_t hist_cap;
     int32_t pad0;
@@ -156,8 +171,7 @@ struct stan_handle {
     int32_t n_mat = 0, max_mat_index = 0;
     bool have_mesh = false, have_mat = false, have_dof = false, assembled = false, solved = false,
          recovered = false;
-    std::vector<int32_t> h_conn;        // kept for the native AssignDOF only
-    std::vector<int32_t> h_node_index;  // host copy of the dof map (RHS assembly, partitioning)
+    std::vector<int32_t> h_conn;        // host copy of the connectivity, fetched back only if the host AssignDOF runs
     stan::DevBuf<double> d_xyz;         // 3*n_nodes
     stan::DevBuf<int32_t> d_conn;       // 8*n_elem
     stan::DevBuf<uint8_t> d_etype;      // n_elem
@@ -173,6 +187,7 @@ struct stan_handle {
     // ---- partition ----
     int64_t row0 = 0, row1 = 0;         // owned BFS rows [row0, row1)
     int64_t n_halo = 0;                 // halo nodes appended after the owned rows in x vectors
+    int64_t nloc_pad = 0;               // node index where the halo tail starts: nloc (1 GPU) or nloc rounded up to HALO_ALIGN
     int64_t elem0 = 0, elem1 = 0;       // elements whose strain/stress this rank recovers
 
     // ---- assembled system (local rows) ----
@@ -200,6 +215,7 @@ struct stan_handle {
     stan::DevBuf<double> d_hist;        // 4 doubles per iteration (stan_set_cg_history)
     int32_t hist_cap = 0, hist_count = 0;
     bool x_in_alt = false;
+    double *sol = nullptr;              // accepted solution of the last solve (owned rows), wherever the solver keeps it
     unsigned long long red_seq = 0;     // cross-rank reductions published so far (peer-memory mode)
 
     // ---- results ----
@@ -208,7 +224,7 @@ struct stan_handle {
     stan::DevBuf<float> d_cell, d_point;      // post-processing scalars: [elem][24][3], [node][24]
     bool postprocessed = false;
 
-    stan::ScratchSlot scratch[12];      // see ScratchBuf: 0-5 pattern/halo/assembly temporaries, 6-7 element maps, 8 scan
+    stan::ScratchSlot scratch[12];      // see ScratchBuf: 0-5 pattern/halo/assembly temporaries, 6-7 element maps, 8 scan, 9 checks
     stan::CgState *h_state = nullptr;   // pinned mirror of the device CG state
     stan::Comm *comm = nullptr;
     int64_t launches = 0;
@@ -257,7 +273,10 @@ int comm_unique_id(void *id128);
 int comm_init(stan_handle *h, const void *id128);
 void comm_destroy(stan_handle *h);
 int comm_allreduce_sum(stan_handle *h, double *d_buf, int count, cudaStream_t s);
-int comm_halo_exchange(stan_handle *h, double *d_vec, cudaStream_t s, CgState *st = nullptr);
+int comm_halo_exchange(stan_handle *h, double *d_vec, int vec_id, cudaStream_t s, CgState *st);
+int comm_cg_vectors(stan_handle *h, double **p, double **x, double **xalt, cudaStream_t s);
+bool comm_halo_args(const stan_handle *h, int vec_id, HaloArgs *out);
+unsigned long long comm_next_epoch(stan_handle *h);
 int comm_allgather_rows(stan_handle *h, const double *d_local, double *d_full, cudaStream_t s);
 int comm_build_halo(stan_handle *h);
 bool comm_p2p_active(const stan_handle *h);

@@ -147,6 +147,12 @@ __global__ void k_wide_rows(int n_wide, const int32_t *__restrict__ wide_rows, c
     }
 }
 
+__global__ void k_gather_i32(int64_t n, const int32_t *__restrict__ idx, const int32_t *__restrict__ src,
+                             int32_t *__restrict__ out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) out[t] = src[idx[t]];
+}
+
 __global__ void k_group_max(int64_t nloc, int rows_per_group, const int32_t *__restrict__ brow_ptr, int32_t *out) {
     int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t r0 = g * rows_per_group;
@@ -341,20 +347,29 @@ int build_system_pattern(stan_handle *h) {
 // F (Solver.cs:136-152).  Loads are accumulated on the host in list order (the += of the
 // reference), one value per DOF is uploaded and scattered into the full-space vector.
 int build_rhs(stan_handle *h) {
-    const std::vector<int32_t> &h_node_index = h->h_node_index;
     cudaStream_t s = h->stream;
     const int64_t nloc = h->row1 - h->row0;
     STAN_TRY(h->d_b.alloc(3 * nloc, s));
     STAN_CUDA(cudaMemsetAsync(h->d_b.p, 0, 3 * nloc * sizeof(double), s));
     const int64_t nl = (int64_t)h->h_load_node.size();
     if (!nl) return STAN_OK;
+    std::vector<int32_t> h_node_index((size_t)nl);        // DOF index of the loaded nodes only, position i <-> load entry i
+    {
+        ScratchBuf<int32_t> dn(&h->scratch[2]), di(&h->scratch[3]);
+        STAN_TRY(dn.alloc(nl, s)); STAN_TRY(di.alloc(nl, s));
+        STAN_CUDA(cudaMemcpyAsync(dn.p, h->h_load_node.data(), nl * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        k_gather_i32<<<div_up(nl, 256), 256, 0, s>>>(nl, dn.p, h->d_node_index.p, di.p);
+        STAN_CUDA(cudaMemcpyAsync(h_node_index.data(), di.p, nl * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        STAN_CUDA(cudaStreamSynchronize(s));
+        h->launches += 1;
+    }
     std::unordered_map<int64_t, size_t> slot;
     std::vector<int64_t> dofs;
     std::vector<double> vals;
     slot.reserve((size_t)nl * 3);
     for (int64_t i = 0; i < nl; i++)
         for (int d = 0; d < 3; d++) {
-            int64_t dof = 3 * (int64_t)h_node_index[h->h_load_node[i]] + d;
+            int64_t dof = 3 * (int64_t)h_node_index[i] + d;
             auto it = slot.find(dof);
             if (it == slot.end()) { slot.emplace(dof, dofs.size()); dofs.push_back(dof); vals.push_back(0.0 + h->h_load_val[3 * i + d]); }
             else vals[it->second] += h->h_load_val[3 * i + d];

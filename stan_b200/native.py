@@ -72,6 +72,10 @@ SYMBOLS = {
     "stan_solve_cholesky": (C.c_int, [_P, C.POINTER(CholReport)]),
     "stan_recover": (C.c_int, [_P, C.POINTER(RecoveryStats)]),
     "stan_get_displacements": (C.c_int, [_P, _P]),
+    "stan_get_displacements_local": (C.c_int, [_P, _P]),
+    "stan_get_node_displacements": (C.c_int, [_P, _P]),
+    "stan_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "stan_host_free": (C.c_int, [_P]),
     "stan_get_strain_stress": (C.c_int, [_P, _P, _P]),
     "stan_get_element_range": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
     "stan_postprocess": (C.c_int, [_P, C.POINTER(C.c_double)]),

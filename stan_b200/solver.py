@@ -40,18 +40,59 @@ class LinearStaticsResult:
 class Solver:
     """One handle = one GPU.  Not re-entrant (the reference's solver is single-threaded too)."""
 
-    def __init__(self, device: int = -1, rank: int = 0, world: int = 1):
+    def __init__(self, device: int = -1, rank: int = 0, world: int = 1, pinned_results: bool = False):
+        """pinned_results: result arrays (U, displacements, strain, stress) live in page-locked buffers owned by
+        this Solver and are REUSED by the next call — the device-to-host copies become plain DMA transfers."""
         self._lib = native.load()
         self._h = C.c_void_p()
         opts = native.Options(device, rank, world, 0)
         native.check(self._lib.stan_create(C.byref(opts), C.byref(self._h)))
         self.model: Model | None = None
         self.node_index: np.ndarray | None = None
+        self.world = world
+        self._pinned_results = pinned_results
+        self._pinned = []                # (pointer, array) pairs from stan_host_alloc, freed by close()
+        self._out = {}                   # name -> persistent result buffer
 
     def close(self):
         if self._h:
+            self._out.clear()
+            for ptr, _ in self._pinned:
+                self._lib.stan_host_free(ptr)
+            self._pinned.clear()
             self._lib.stan_destroy(self._h)
             self._h = C.c_void_p()
+
+    def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:
+        """numpy array in page-locked host memory (stan_host_alloc); valid until close()."""
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        ptr = C.c_void_p()
+        native.check(self._lib.stan_host_alloc(max(nbytes, 1), C.byref(ptr)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned.append((ptr, arr))
+        return arr
+
+    def pinned_model(self, m: Model) -> Model:
+        """Copy of the model whose arrays are page-locked: SetModel/SetDOF then upload by DMA without staging."""
+        import dataclasses
+        kw = {}
+        for f in dataclasses.fields(m):
+            v = getattr(m, f.name)
+            if isinstance(v, np.ndarray):
+                a = self.pinned_empty(v.shape, v.dtype)
+                a[...] = v
+                v = a
+            kw[f.name] = v
+        return Model(**kw)
+
+    def _result(self, name, shape, dtype=np.float64):
+        if not self._pinned_results:
+            return np.empty(shape, dtype=dtype)
+        a = self._out.get(name)
+        if a is None or a.shape != tuple(shape) or a.dtype != np.dtype(dtype):
+            a = self._out[name] = self.pinned_empty(shape, dtype)
+        return a
 
     def __del__(self):
         try:
@@ -120,9 +161,22 @@ class Solver:
     # ---- results / inspection ----
     def Include_BC_DOF(self) -> np.ndarray:
         """U_Full (SolverFunctions.cs:520-538): displacement per DOF with zeros at SPC DOFs."""
-        u = np.zeros(self.model.n_dof)
+        u = self._result("U", (self.model.n_dof,))
         native.check(self._lib.stan_get_displacements(self._h, _p(u)))
         return u
+
+    def displacements_local(self) -> np.ndarray:
+        """U of the rows this rank owns ((last_row - first_row) x 3); all of U on one GPU."""
+        r0, r1 = self.partition()
+        u = self._result("U_local", (r1 - r0, 3))
+        native.check(self._lib.stan_get_displacements_local(self._h, _p(u)))
+        return u
+
+    def node_displacements(self) -> np.ndarray:
+        """Node.dU_buffer per node in NodeLib order (Solver.cs:171-178), gathered through the DOF map on the device."""
+        d = self._result("disp", (self.model.n_nodes, 3))
+        native.check(self._lib.stan_get_node_displacements(self._h, _p(d)))
+        return d
 
     def Exclude_BC_DOF(self) -> np.ndarray:
         n, _ = self.csr_upper_size()
@@ -139,7 +193,7 @@ class Solver:
         """Strain[1]/Stress[1] of this rank's element slice (all elements on one GPU)."""
         e0, e1 = self.element_range()
         ne = e1 - e0
-        strain, stress = np.empty((ne, 8, 6)), np.empty((ne, 8, 6))
+        strain, stress = self._result("strain", (ne, 8, 6)), self._result("stress", (ne, 8, 6))
         native.check(self._lib.stan_get_strain_stress(self._h, _p(strain), _p(stress)))
         return strain, stress
 
@@ -228,7 +282,9 @@ class Solver:
 
     # ---- the driver: Solver.SolverLinearStatics (Solver.cs:71-217) ----
     def SolverLinearStatics(self, m: Model, *, node_index=None, merit_check=1, time_kernels=0,
-                            fetch=True) -> LinearStaticsResult:
+                            fetch=True, local_rows=False) -> LinearStaticsResult:
+        """local_rows (several GPUs): U_full holds only the rows this rank owns (partition() x 3) and disp is None —
+        the caller merges the ranks' slices, as it already does for the strain/stress slices."""
         self.SetModel(m)
         if node_index is None:
             self.AssignDOF()
@@ -244,9 +300,11 @@ class Solver:
         rec = self.Recovery_Stress()
         if not fetch:
             return LinearStaticsResult(self.node_index, None, None, None, None, a, cg, rec)
-        U = self.Include_BC_DOF()
         strain, stress = self.strain_stress()
-        disp = U.reshape(-1, 3)[self.node_index]
+        if local_rows:
+            return LinearStaticsResult(self.node_index, self.displacements_local(), None, strain, stress, a, cg, rec)
+        U = self.Include_BC_DOF()
+        disp = self.node_displacements()
         return LinearStaticsResult(self.node_index, U, disp, strain, stress, a, cg, rec)
 
 

@@ -5,9 +5,10 @@ The oracle is a restatement (PARITY UNPINNED, see oracle/stan_oracle.c): "matche
 "matches the CPU restatement of STAN", not "matches a STAN binary".
 
 Bars (BASELINE.json north_star): DOF numbering and CSR pattern bit-exact, displacements 1e-10 relative and
-stresses 1e-8 relative at an identical CG tolerance.  An iterative solve to tolerance t only determines U to
-about t (two runs that both satisfy ||r|| <= t ||b|| may differ by that much), so the 1e-10 bar is checked with
-EpsF = 1e-11: one decade of margin, still above the FP64 floor of these systems.
+stresses 1e-8 relative at an identical CG tolerance.  The tolerance is EpsF = 1e-9: the tightest these beams
+reach in FP64 (the true residual of the 100k beam stalls near 1e-8..1e-9 * ||b|| when asked for 1e-10; measured
+with the oracle, tools/cg_trajectory.py).  U is far better determined than the residual suggests — the load excites
+the softest modes, so two converged runs agree to ~1e-12 — which is what makes the 1e-10 bar testable.
 """
 import numpy as np
 import pytest
@@ -32,7 +33,7 @@ def _rel(a, b):
 def test_beam_100k_g2_full_oracle_run(solver, oracle):
     """BASELINE config 2 (20x20x250 G2, 332 073 DOF): the whole path on both sides, strict CG."""
     oracle.set_threads()
-    m = mesh.workload("beam_100k_g2", tolerance=1e-11)
+    m = mesh.workload("beam_100k_g2", tolerance=1e-9)
     solver.SetModel(m)
     ni = solver.AssignDOF()
     assert np.array_equal(ni, oracle.assign_dof(m))                       # R0 bit-exact at size
@@ -47,10 +48,16 @@ def test_beam_100k_g2_full_oracle_run(solver, oracle):
     assert np.array_equal(rp, orp) and np.array_equal(col, ocol)          # R3 pattern bit-exact (13.6 M entries)
     assert np.abs(val - oval).max() <= 1e-12 * np.abs(oval).max()         # R2+R3 values
     rep = solver.LinearSolver_CG(merit_check=0, IterMax=5000)             # R5, strict
-    xo, orep = oracle.lincg(K, F, oracle.cg_opts(epsf=1e-11, merit_check=0, maxits=5000, parallel_spmv=1))
+    xo, orep = oracle.lincg(K, F, oracle.cg_opts(epsf=1e-9, merit_check=0, maxits=5000, parallel_spmv=1))
     assert rep.terminationtype == 1 and orep.terminationtype == 1
-    assert abs(rep.iterationscount - orep.iterationscount) <= 0.1 * orep.iterationscount   # see test_cg_trajectory
+    # the oracle's own roundings need 1195 .. 1417 iterations here (profiles/r02_cg_trajectory_100k.json)
+    assert abs(rep.iterationscount - orep.iterationscount) <= 0.25 * orep.iterationscount
     xg = solver.Exclude_BC_DOF()
+    # R5 alone: the oracle's CG on the very matrix the device assembled
+    xs, srep = oracle.lincg(oracle.UpperCsr.from_arrays(rp, col, val), F,
+                            oracle.cg_opts(epsf=1e-9, merit_check=0, maxits=5000, parallel_spmv=1))
+    assert srep.terminationtype == 1 and _rel(xg, xs) < 1e-10
+    # whole path: device-assembled against oracle-assembled matrix
     assert _rel(xg, xo) < 1e-10
     solver.Recovery_Stress()                                              # R4
     strain, stress = solver.strain_stress()
@@ -117,10 +124,10 @@ def test_example1_analogue_alglib_defaults(solver, oracle):
     assert _rel(r.U_full, o.U_full) < 1e-8
     assert np.abs(r.stress - o.stress).max() <= 5e-7 * np.abs(o.stress).max()
     # strict twin at the north_star bars
-    m.tolerance = 1e-11
+    m.tolerance = 1e-9
     m.max_iter = 5000
     r = solver.SolverLinearStatics(m, merit_check=0)
-    o = oracle.linear_statics(m, oracle.cg_opts(epsf=1e-11, maxits=5000, merit_check=0))
+    o = oracle.linear_statics(m, oracle.cg_opts(epsf=1e-9, maxits=5000, merit_check=0))
     assert r.cg.terminationtype == 1 and o.stats.cg.terminationtype == 1
     assert _rel(r.U_full, o.U_full) < 1e-10
     assert np.abs(r.stress - o.stress).max() <= 1e-8 * np.abs(o.stress).max()

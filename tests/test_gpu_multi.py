@@ -1,4 +1,6 @@
-"""Partitioned solve on 2 GPUs (NCCL halo exchange + all-reduced dots) against the single-GPU solve."""
+"""Partitioned solve on 2 GPUs against the single-GPU solve: the default peer-memory data plane with the halo
+exchange fused into the product kernel, the stand-alone push / wait kernels behind the fallback SpMV, and the
+NCCL data plane (halo send/recv + all-reduced dots)."""
 import os
 import subprocess
 import sys
@@ -9,11 +11,12 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_gpu_partition_matches_single_gpu():
+@pytest.mark.parametrize("env", [{}, {"STAN_SPMV": "0"}, {"STAN_COMM": "nccl"}], ids=["fused_halo", "push_wait_kernels", "nccl"])
+def test_two_gpu_partition_matches_single_gpu(env):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29631", os.path.join("tools", "multi_gpu_check.py"), "10", "8", "40"]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env={**os.environ, **env})
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

@@ -357,7 +357,7 @@ def test_rows_of_any_width(solver, oracle):
     ni, red, K = _assembled(solver, oracle, m)
     rp, col, val = solver.csr_upper()
     orp, ocol, oval = K.arrays()
-    assert np.diff(orp).max() > 3 * 96
+    assert np.diff(orp).max() > 200                 # upper-triangle part of a 369-entry row
     assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
     assert np.abs(val - oval).max() <= 1e-12 * np.abs(oval).max()
     xr = np.random.default_rng(4).standard_normal(K.n)
