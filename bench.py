@@ -298,6 +298,8 @@ def run_ours(args):
         + m.spc_val.nbytes + m.load_node.nbytes + m.load_val.nbytes + m.mat_E.nbytes + m.mat_nu.nbytes
     tip = ni[m.load_node]                                 # rows of the loaded (tip) nodes
 
+    m.max_iter = args.cg_maxits                           # same iteration cap as the device-timed steps
+
     def e2e_pass():
         r = s.SolverLinearStatics(m, node_index=ni_pinned, merit_check=0, local_rows=world > 1)
         if world > 1:

@@ -566,15 +566,16 @@ constexpr int T3_THREADS = 32 * (T3_GROUPS * T3_GW + 1);
 template <bool HALO> struct XArg { typedef const double *__restrict__ type; };   // read-only for the whole kernel
 template <> struct XArg<true> { typedef const double *type; };                      // its halo tail is written by peers
 
-template <bool DOT, bool HALO>
+template <bool DOT, bool HALO, bool XPLAIN = HALO>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 k_spmv_tile3(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
-             const double *__restrict__ vals, typename XArg<HALO>::type x, double *__restrict__ y, BulkLayout L,
+             const double *__restrict__ vals, typename XArg<XPLAIN>::type x, double *__restrict__ y, BulkLayout L,
              double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar, HaloArgs ha) {
     if (st && st->done) return;
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ __align__(8) uint64_t s_full[T3_GROUPS], s_empty[T3_GROUPS];
     __shared__ double s_part[T3_GROUPS][T3_PARTS][3 * T3_ROWS];
+    __shared__ int s_tile[T3_GROUPS];                      // HALO: tile held by each ring stage (written by the producer)
 #define X_AT(i) x[i]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nchunks = (nrows + T3_ROWS - 1) / T3_ROWS;
@@ -592,51 +593,36 @@ k_spmv_tile3(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t 
 
     double dsum = 0.0;
     if (warp == T3_GROUPS * T3_GW) {
-        // ---- producer ----
-        auto issue = [&](int64_t i) {                      // lane 0 only
-            const int g = (int)(i % T3_GROUPS);
-            const int64_t k = i / T3_GROUPS;
-            if (k > 0) mbar_wait(&s_empty[g], (uint32_t)((k - 1) & 1));
-            const int64_t r0 = tile_of(i) * T3_ROWS;
-            const int64_t r1 = (r0 + T3_ROWS < nrows) ? r0 + T3_ROWS : nrows;
-            unsigned char *base = s_raw + (size_t)g * L.stage_bytes;
-            const int64_t b0 = brow_ptr[r0], b1 = brow_ptr[r1];
-            const int64_t voff = 72 * b0, voff_al = voff & ~(int64_t)15;
-            const uint32_t vbytes = (uint32_t)(((voff - voff_al) + 72 * (b1 - b0) + 15) & ~(int64_t)15);
-            const int64_t coff = 4 * b0, coff_al = coff & ~(int64_t)15;
-            const uint32_t cbytes = (uint32_t)(((coff - coff_al) + 4 * (b1 - b0) + 15) & ~(int64_t)15);
-            const uint32_t rbytes = (uint32_t)((4 * (r1 - r0 + 1) + 15) & ~(int64_t)15);
-            mbar_expect_tx(&s_full[g], vbytes + cbytes + rbytes);
-            bulk_g2s(base + L.vals_off, (const unsigned char *)vals + voff_al, vbytes, &s_full[g]);
-            bulk_g2s(base + L.cols_off, (const unsigned char *)bcol + coff_al, cbytes, &s_full[g]);
-            bulk_g2s(base + L.rp_off, (const unsigned char *)(brow_ptr + r0), rbytes, &s_full[g]);
-        };
-        const int64_t first = my_n < T3_GROUPS ? my_n : T3_GROUPS;
-        if (lane == 0)
-            for (int64_t i = 0; i < first; i++) issue(i);
-        if (HALO) {                                        // the whole warp pushes while the consumers start
-            const CommDev *cd = ha.cd;
-            const int W = cd->world, me = cd->rank;
-            const long long n3 = 3 * cd->send_off[W];
-            int peer = 0;
-            for (long long t = blockIdx.x * 32ll + lane; t < n3; t += 32ll * gridDim.x) {
-                const long long i = t / 3;
-                while (i >= cd->send_off[peer + 1]) peer++;          // t only grows
-                cd->vec[peer][ha.vec_id][cd->tail_off[peer] + 3 * (i - cd->send_off[peer]) + (t - 3 * i)] =
-                    x[3 * (long long)cd->send_rows[i] + (t - 3 * i)];
-            }
-            __threadfence_system();
-            __syncwarp();
-            unsigned int ticket = 0;
-            if (lane == 0) ticket = atomicInc(cd->ticket, gridDim.x - 1);
-            ticket = __shfl_sync(0xffffffffu, ticket, 0);
-            if (ticket == gridDim.x - 1 && lane < W && lane != me && cd->send_off[lane + 1] > cd->send_off[lane]) {
-                __threadfence_system();
-                *(volatile unsigned long long *)&cd->ctrl[lane]->hflag[me] = expect;
+        // ---- producer (lane 0) ----
+        // Three groups finish a tile every ~1.3 us between them, so nothing on this loop's path may wait for
+        // global memory: the tile id is fetched two tiles ahead and the row pointers one tile ahead.
+        if (lane == 0 && my_n > 0) {
+            int64_t tile_a = tile_of(0), tile_b = my_n > 1 ? tile_of(1) : 0;      // tiles i and i + 1
+            int64_t r0 = tile_a * T3_ROWS, r1 = (r0 + T3_ROWS < nrows) ? r0 + T3_ROWS : nrows;
+            int64_t b0 = brow_ptr[r0], b1 = brow_ptr[r1];
+            for (int64_t i = 0; i < my_n; i++) {
+                const int g = (int)(i % T3_GROUPS);
+                const int64_t k = i / T3_GROUPS;
+                const int64_t tile_c = i + 2 < my_n ? tile_of(i + 2) : 0;
+                const int64_t nr0 = tile_b * T3_ROWS, nr1 = (nr0 + T3_ROWS < nrows) ? nr0 + T3_ROWS : nrows;
+                int64_t nb0 = 0, nb1 = 0;
+                if (i + 1 < my_n) { nb0 = brow_ptr[nr0]; nb1 = brow_ptr[nr1]; }
+                if (k > 0) mbar_wait(&s_empty[g], (uint32_t)((k - 1) & 1));
+                if (HALO) s_tile[g] = (int)tile_a;         // published by the arrive.expect_tx (release) that follows
+                unsigned char *base = s_raw + (size_t)g * L.stage_bytes;
+                const int64_t voff = 72 * b0, voff_al = voff & ~(int64_t)15;
+                const uint32_t vbytes = (uint32_t)(((voff - voff_al) + 72 * (b1 - b0) + 15) & ~(int64_t)15);
+                const int64_t coff = 4 * b0, coff_al = coff & ~(int64_t)15;
+                const uint32_t cbytes = (uint32_t)(((coff - coff_al) + 4 * (b1 - b0) + 15) & ~(int64_t)15);
+                const uint32_t rbytes = (uint32_t)((4 * (r1 - r0 + 1) + 15) & ~(int64_t)15);
+                mbar_expect_tx(&s_full[g], vbytes + cbytes + rbytes);
+                bulk_g2s(base + L.vals_off, (const unsigned char *)vals + voff_al, vbytes, &s_full[g]);
+                bulk_g2s(base + L.cols_off, (const unsigned char *)bcol + coff_al, cbytes, &s_full[g]);
+                bulk_g2s(base + L.rp_off, (const unsigned char *)(brow_ptr + r0), rbytes, &s_full[g]);
+                tile_a = tile_b; tile_b = tile_c;
+                r0 = nr0; r1 = nr1; b0 = nb0; b1 = nb1;
             }
         }
-        if (lane == 0)
-            for (int64_t i = first; i < my_n; i++) issue(i);
     } else {
         const int g = warp / T3_GW, wg = warp % T3_GW;     // ---- consumers ----
         const int part = wg / 3, t = (wg % 3) * 32 + lane; // scalar row of the tile
@@ -644,6 +630,36 @@ k_spmv_tile3(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t 
         const unsigned char *base = s_raw + (size_t)g * L.stage_bytes;
         const int32_t *rp = reinterpret_cast<const int32_t *>(base + L.rp_off);
         bool halo_ready = !HALO;
+        if (HALO) {
+            // Push: all 27 consumer warps, while the producer's first bulk copies are still in flight.  A thread
+            // handles about one entry: one index load, one x load, one NVLink store.
+            constexpr int NC = 32 * T3_GROUPS * T3_GW;
+            const CommDev *cd = ha.cd;
+            const int W = cd->world, me = cd->rank;
+            for (int peer = 0; peer < W; peer++) {
+                const long long lo3 = 3 * cd->send_off[peer], hi3 = 3 * cd->send_off[peer + 1];
+                if (hi3 == lo3) continue;
+                double *dst = cd->vec[peer][ha.vec_id] + cd->tail_off[peer] - lo3;
+                const int32_t *rows = cd->send_rows;
+                for (long long e = lo3 + (long long)blockIdx.x * NC + tid; e < hi3; e += (long long)NC * gridDim.x) {
+                    const long long n = e / 3;
+                    dst[e] = x[3 * (long long)rows[n] + (e - 3 * n)];
+                }
+            }
+            // one system-scope fence per CTA, by the thread that takes the ticket, after a barrier that orders
+            // every consumer's stores before it (fences are cumulative; 864 threads fencing individually cost
+            // ~60 us per launch)
+            asm volatile("bar.sync 5, %0;" ::"n"(NC) : "memory");
+            if (tid == 0) {
+                __threadfence_system();
+                if (atomicInc(cd->ticket, gridDim.x - 1) == gridDim.x - 1) {
+                    __threadfence_system();                // acquire side: every CTA fenced before its ticket
+                    for (int peer = 0; peer < W; peer++)
+                        if (peer != me && cd->send_off[peer + 1] > cd->send_off[peer])
+                            *(volatile unsigned long long *)&cd->ctrl[peer]->hflag[me] = expect;
+                }
+            }
+        }
         for (int64_t i = g, k = 0; i < my_n; i += T3_GROUPS, k++) {
             if (HALO && !halo_ready && blockIdx.x + i * (int64_t)gridDim.x >= ha.n_interior) {
                 const CommDev *cd = ha.cd;                 // first tile with halo columns: wait for the neighbours
@@ -660,7 +676,7 @@ k_spmv_tile3(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t 
                 halo_ready = true;
             }
             mbar_wait(&s_full[g], (uint32_t)(k & 1));
-            const int64_t r0 = tile_of(i) * T3_ROWS;
+            const int64_t r0 = (HALO ? (int64_t)s_tile[g] : blockIdx.x + i * (int64_t)gridDim.x) * T3_ROWS;
             const int nr = (int)((nrows - r0) < T3_ROWS ? (nrows - r0) : T3_ROWS);
             double acc = 0.0;
             if (br < nr) {
@@ -861,6 +877,7 @@ static int spmv_plan(const stan_handle *h, int64_t nrows, SpmvPlan *p) {
             STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
             STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
             STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
+            STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
             const int64_t nchunks = (nrows + T3_ROWS - 1) / T3_ROWS;
             p->grid = (int)(nchunks < h->sm_count ? (nchunks > 0 ? nchunks : 1) : h->sm_count);
             return STAN_OK;
@@ -914,7 +931,11 @@ static void launch_spmv(const stan_handle *h, const SpmvPlan &p, bool dot, int64
         nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out, p.L, partials, counter, st, slot, step, run_scalar)
     if (p.variant == 4) {
         const HaloArgs none = {nullptr, nullptr, 0, 0};
-        if (ha)
+        const char *nc = getenv("STAN_HALO_NC");           // experiment: read-only (ld.global.nc) x loads in the fused kernel
+        if (ha && nc && atoi(nc) == 1)
+            k_spmv_tile3<true, true, false><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
+                                                                               p.L, partials, counter, st, slot, step, run_scalar, *ha);
+        else if (ha)
             k_spmv_tile3<true, true><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
                                                                         p.L, partials, counter, st, slot, step, run_scalar, *ha);
         else if (dot)
@@ -995,7 +1016,12 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     STAN_CUDA(cudaMemcpyAsync(h->d_state.p, hst, sizeof(CgState), cudaMemcpyHostToDevice, s));
     CgState *st = h->d_state.p;
     double *x = vx, *xalt = vxalt;
-    const bool fused_halo = p2p && plan.variant == 4;      // the product kernel exchanges its own halo
+    // STAN_FUSED_HALO=1: the product kernel exchanges its own halo, overlapped with the tiles that need none.
+    // Measured (profiles/r02_multi_gpu_iteration.md) it is within +-1 % of the two small push / wait launches on
+    // 2 and 8 GPUs — the iteration is bound by the three cross-rank synchronisations, not by the halo bytes —
+    // and 1 % slower on 8, so the stand-alone kernels are the default.
+    const char *fh = getenv("STAN_FUSED_HALO");
+    const bool fused_halo = p2p && plan.variant == 4 && fh && atoi(fh) == 1;
     int64_t launches = 0;
     int spmv_launches = 0;
     float spmv_ms = 0.f;
@@ -1073,7 +1099,9 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
         return STAN_OK;
     };
     static const bool graphs_on = !(getenv("STAN_GRAPH") && atoi(getenv("STAN_GRAPH")) == 0);
-    const bool use_graph = graphs_on && !multi && !timek;
+    // replayable when no launch argument changes between batches: one GPU, or peer-memory mode (all sequence
+    // numbers live in the device state; the NCCL data plane is enqueued call by call)
+    const bool use_graph = graphs_on && !timek && (!multi || p2p);
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
     int64_t launches_per_batch = 0;

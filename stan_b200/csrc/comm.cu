@@ -194,11 +194,13 @@ k_halo_push(const CommDev *__restrict__ cd, const double *__restrict__ vec, int 
             cd->vec[peer][vec_id][cd->tail_off[peer] + 3 * (i - cd->send_off[peer]) + (t - 3 * i)] =
                 vec[3 * (long long)cd->send_rows[i] + (t - 3 * i)];
         }
-        __threadfence_system();
     }
     __shared__ bool last;
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicInc(cd->ticket, gridDim.x - 1) == gridDim.x - 1);
+    if (threadIdx.x == 0) {                                // one fence per CTA, cumulative over the CTA's stores
+        __threadfence_system();
+        last = (atomicInc(cd->ticket, gridDim.x - 1) == gridDim.x - 1);
+    }
     __syncthreads();
     if (last && !skip && threadIdx.x < W && threadIdx.x != me && cd->send_off[threadIdx.x + 1] > cd->send_off[threadIdx.x]) {
         __threadfence_system();

@@ -1,6 +1,7 @@
-"""Partitioned solve on 2 GPUs against the single-GPU solve: the default peer-memory data plane with the halo
-exchange fused into the product kernel, the stand-alone push / wait kernels behind the fallback SpMV, and the
-NCCL data plane (halo send/recv + all-reduced dots)."""
+"""Partitioned solve on 2 GPUs against the single-GPU solve: the default peer-memory data plane (push / wait
+kernels storing straight into the neighbours' vector tails, flag-carrying reductions), the variant with the halo
+exchange fused into the product kernel, the warp-per-row fallback SpMV, and the NCCL data plane (halo send/recv +
+all-reduced dots)."""
 import os
 import subprocess
 import sys
@@ -11,7 +12,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("env", [{}, {"STAN_SPMV": "0"}, {"STAN_COMM": "nccl"}], ids=["fused_halo", "push_wait_kernels", "nccl"])
+@pytest.mark.parametrize("env", [{}, {"STAN_FUSED_HALO": "1"}, {"STAN_SPMV": "0"}, {"STAN_COMM": "nccl"}],
+                         ids=["push_wait_kernels", "fused_halo", "fallback_spmv", "nccl"])
 def test_two_gpu_partition_matches_single_gpu(env):
     import torch
     if torch.cuda.device_count() < 2:
