@@ -19,26 +19,38 @@ namespace {
 __constant__ double c_rdNl[9][24];   // same table as assembly.cu (per-TU constant copy)
 __constant__ double c_N[8][8];       // N[i][g], HEX8_ShapeFunctions(node i, 1/sqrt(3)) FE_Library.cs:285-321
 
-constexpr int REC_THREADS = 128;     // 16 elements per CTA
+constexpr int REC_THREADS = 256;     // 32 elements per CTA
 
-__global__ void __launch_bounds__(REC_THREADS, 4)
+// IEEE operations that the compiler may not contract into FMAs: like the element stiffness (assembly.cu), strain
+// and stress follow the reference's operation order exactly — MatrixST.MultiplyVector sums j ascending, and a
+// product with a structural zero of BL or D leaves the sum unchanged — so for the same U they are BIT-IDENTICAL
+// to the CPU restatement.
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+
+__global__ void __launch_bounds__(REC_THREADS, 3)
 k_recover(int64_t e_first, int64_t e_count, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
           const int32_t *__restrict__ node_index, const uint8_t *__restrict__ etype, const int32_t *__restrict__ emat,
           const double *__restrict__ lam_tab, const double *__restrict__ G_tab, const double *__restrict__ ufull,
           double *__restrict__ strain, double *__restrict__ stress, int32_t *err,
           const int32_t *__restrict__ elem_list = nullptr) {
-    // 13-double rows: with 12 the four elements of a warp (96-double stride) sat on the same banks and
-    // every extrapolation read was a 4-way conflict (ncu: 359 M shared bank conflicts at 10M elements)
+    // per element: 8 nodes x (x, y, z, ux, uy, uz); 49-double rows keep the 4 elements of a warp on distinct banks
+    __shared__ double s_xu[REC_THREADS / 8][49];
+    // Gauss-point strains (6) and stresses (6); 13-double rows for the same reason
     __shared__ double s_val[REC_THREADS / 8][8][13];
+    __shared__ double s_tab[9 * 24];               // dN_dLocal: lanes index it by their own Gauss point
+    __shared__ double s_N[64];
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t el = t >> 3;                         // local element index
     const int g = (int)(t & 7), le = threadIdx.x >> 3;
     const bool valid = el < e_count;
     const int64_t e = !valid ? 0 : (elem_list ? (int64_t)elem_list[el] : e_first + el);   // global element index
-    int type = STAN_HEX8_G2;
+    if (threadIdx.x < 216) s_tab[threadIdx.x] = (&c_rdNl[0][0])[threadIdx.x];
+    if (threadIdx.x < 64) s_N[threadIdx.x] = (&c_N[0][0])[threadIdx.x];
     // the 8 threads of an element fetch one node each (coordinates and displacement, Element.cs:214-221)
-    // and share them through shared memory; 49-double stride keeps the 4 elements of a warp on distinct banks
-    __shared__ double s_xu[REC_THREADS / 8][49];
+    int type = STAN_HEX8_G2;
+    double lam = 0.0, G = 0.0;
     if (valid) {
         const int32_t nd = conn[8 * e + g];
         const double *p = xyz + 3 * (int64_t)nd;
@@ -46,78 +58,76 @@ k_recover(int64_t e_first, int64_t e_count, const int32_t *__restrict__ conn, co
         double *d = s_xu[le];
         d[3 * g] = p[0]; d[3 * g + 1] = p[1]; d[3 * g + 2] = p[2];
         d[24 + 3 * g] = u[0]; d[24 + 3 * g + 1] = u[1]; d[24 + 3 * g + 2] = u[2];
+        type = etype[e];
+        const int mat = emat[e];
+        lam = lam_tab[mat]; G = G_tab[mat];
     }
     __syncthreads();
-    if (valid) {
-        type = etype[e];
-        double val[12];
+    if (valid && (type == STAN_HEX8_G2 || g == 0)) {
+        const double *tab = s_tab + 24 * ((type == STAN_HEX8_G2) ? g : 8);
+        const double *X = s_xu[le], *U = s_xu[le] + 24;
+        double J[9];                                   // J = dN_dLocal * X, k ascending (Element.cs:274-292)
 #pragma unroll
-        for (int c = 0; c < 12; c++) val[c] = 0.0;
-        if (type == STAN_HEX8_G2 || g == 0) {
-            const int gp = (type == STAN_HEX8_G2) ? g : 8;
-            double X[24], U[24];
+        for (int r = 0; r < 3; r++)
 #pragma unroll
-            for (int k = 0; k < 24; k++) { X[k] = s_xu[le][k]; U[k] = s_xu[le][24 + k]; }
-            double J[9];
+            for (int c = 0; c < 3; c++) {
+                double sum = mul(tab[r * 8], X[c]);
 #pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) s += c_rdNl[gp][r * 8 + k] * X[k * 3 + c];
-                    J[r * 3 + c] = s;
-                }
-            const double det = J[0] * J[4] * J[8] + J[3] * J[7] * J[2] + J[6] * J[1] * J[5] - J[2] * J[4] * J[6] -
-                               J[0] * J[5] * J[7] - J[8] * J[1] * J[3];
-            if (det == 0.0) atomicOr(err + 2, 1);
-            const double inv = 1.0 / det;
-            double Ji[9];
-            Ji[0] = inv * (J[4] * J[8] - J[5] * J[7]);
-            Ji[1] = inv * (J[2] * J[7] - J[1] * J[8]);
-            Ji[2] = inv * (J[1] * J[5] - J[2] * J[4]);
-            Ji[3] = inv * (J[5] * J[6] - J[3] * J[8]);
-            Ji[4] = inv * (J[0] * J[8] - J[2] * J[6]);
-            Ji[5] = inv * (J[2] * J[3] - J[0] * J[5]);
-            Ji[6] = inv * (J[3] * J[7] - J[4] * J[6]);
-            Ji[7] = inv * (J[1] * J[6] - J[0] * J[7]);
-            Ji[8] = inv * (J[0] * J[4] - J[1] * J[3]);
-            // eps = BL0 dU in node order (BL0_Matrix, Element.cs:316-324; MultiplyVector j ascending)
-            double ex = 0, ey = 0, ez = 0, exy = 0, eyz = 0, exz = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const double dx = Ji[0] * c_rdNl[gp][k] + Ji[1] * c_rdNl[gp][8 + k] + Ji[2] * c_rdNl[gp][16 + k];
-                const double dy = Ji[3] * c_rdNl[gp][k] + Ji[4] * c_rdNl[gp][8 + k] + Ji[5] * c_rdNl[gp][16 + k];
-                const double dz = Ji[6] * c_rdNl[gp][k] + Ji[7] * c_rdNl[gp][8 + k] + Ji[8] * c_rdNl[gp][16 + k];
-                const double ux = U[3 * k], uy = U[3 * k + 1], uz = U[3 * k + 2];
-                ex += dx * ux; ey += dy * uy; ez += dz * uz;
-                exy += dy * ux; exy += dx * uy;
-                eyz += dz * uy; eyz += dy * uz;
-                exz += dz * ux; exz += dx * uz;
+                for (int k = 1; k < 8; k++) sum = add(sum, mul(tab[r * 8 + k], X[k * 3 + c]));
+                J[r * 3 + c] = sum;
             }
-            const int mat = emat[e];
-            const double lam = lam_tab[mat], G = G_tab[mat], d0 = lam + (2 * G);
-            val[0] = ex; val[1] = ey; val[2] = ez; val[3] = exy; val[4] = eyz; val[5] = exz;
-            val[6] = d0 * ex + lam * ey + lam * ez;      // D.MultiplyVector, Material.cs:42-53
-            val[7] = lam * ex + d0 * ey + lam * ez;
-            val[8] = lam * ex + lam * ey + d0 * ez;
-            val[9] = G * exy; val[10] = G * eyz; val[11] = G * exz;
-        }
+        double det = mul(mul(J[0], J[4]), J[8]);       // MatrixST.Det3, MatrixST.cs:274-279
+        det = add(det, mul(mul(J[3], J[7]), J[2]));
+        det = add(det, mul(mul(J[6], J[1]), J[5]));
+        det = sub(det, mul(mul(J[2], J[4]), J[6]));
+        det = sub(det, mul(mul(J[0], J[5]), J[7]));
+        det = sub(det, mul(mul(J[8], J[1]), J[3]));
+        if (det == 0.0) atomicOr(err + 2, 1);
+        const double inv = __ddiv_rn(1.0, det);
+        double Ji[9];                                  // MatrixST.Inverse, MatrixST.cs:303-311
+        Ji[0] = mul(inv, sub(mul(J[4], J[8]), mul(J[5], J[7])));
+        Ji[1] = mul(inv, sub(mul(J[2], J[7]), mul(J[1], J[8])));
+        Ji[2] = mul(inv, sub(mul(J[1], J[5]), mul(J[2], J[4])));
+        Ji[3] = mul(inv, sub(mul(J[5], J[6]), mul(J[3], J[8])));
+        Ji[4] = mul(inv, sub(mul(J[0], J[8]), mul(J[2], J[6])));
+        Ji[5] = mul(inv, sub(mul(J[2], J[3]), mul(J[0], J[5])));
+        Ji[6] = mul(inv, sub(mul(J[3], J[7]), mul(J[4], J[6])));
+        Ji[7] = mul(inv, sub(mul(J[1], J[6]), mul(J[0], J[7])));
+        Ji[8] = mul(inv, sub(mul(J[0], J[4]), mul(J[1], J[3])));
+        // eps = BL0 dU (BL0_Matrix, Element.cs:316-324; MultiplyVector: columns ascending, i.e. node by node, x y z)
+        double ex = 0, ey = 0, ez = 0, exy = 0, eyz = 0, exz = 0;
 #pragma unroll
-        for (int c = 0; c < 12; c++) s_val[le][g][c] = val[c];
+        for (int k = 0; k < 8; k++) {
+            const double t0 = tab[k], t1 = tab[8 + k], t2 = tab[16 + k];
+            const double dx = add(add(mul(Ji[0], t0), mul(Ji[1], t1)), mul(Ji[2], t2));
+            const double dy = add(add(mul(Ji[3], t0), mul(Ji[4], t1)), mul(Ji[5], t2));
+            const double dz = add(add(mul(Ji[6], t0), mul(Ji[7], t1)), mul(Ji[8], t2));
+            const double ux = U[3 * k], uy = U[3 * k + 1], uz = U[3 * k + 2];
+            ex = add(ex, mul(dx, ux)); ey = add(ey, mul(dy, uy)); ez = add(ez, mul(dz, uz));
+            exy = add(exy, mul(dy, ux)); exy = add(exy, mul(dx, uy));
+            eyz = add(eyz, mul(dz, uy)); eyz = add(eyz, mul(dy, uz));
+            exz = add(exz, mul(dz, ux)); exz = add(exz, mul(dx, uz));
+        }
+        const double d0 = add(lam, mul(2.0, G));       // Material.cs:42
+        double *v = s_val[le][g];
+        v[0] = ex; v[1] = ey; v[2] = ez; v[3] = exy; v[4] = eyz; v[5] = exz;
+        v[6] = add(add(mul(d0, ex), mul(lam, ey)), mul(lam, ez));      // D.MultiplyVector, Material.cs:42-53
+        v[7] = add(add(mul(lam, ex), mul(d0, ey)), mul(lam, ez));
+        v[8] = add(add(mul(lam, ex), mul(lam, ey)), mul(d0, ez));
+        v[9] = mul(G, exy); v[10] = mul(G, eyz); v[11] = mul(G, exz);
     }
     __syncthreads();
     if (!valid) return;
     const int i = g;                                     // this thread now owns element node i
     double out[12];
-#pragma unroll
-    for (int c = 0; c < 12; c++) out[c] = 0.0;
     if (type == STAN_HEX8_G2) {
 #pragma unroll
-        for (int q = 0; q < 8; q++) {                    // Element.cs:238-245, g ascending
-            const double w = c_N[i][q];
+        for (int c = 0; c < 12; c++) out[c] = 0.0;
 #pragma unroll
-            for (int c = 0; c < 12; c++) out[c] += s_val[le][q][c] * w;
+        for (int q = 0; q < 8; q++) {                    // Element.cs:238-245, g ascending
+            const double w = s_N[8 * i + q];
+#pragma unroll
+            for (int c = 0; c < 12; c++) out[c] = add(out[c], mul(s_val[le][q][c], w));
         }
     } else {
 #pragma unroll

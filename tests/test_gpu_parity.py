@@ -45,14 +45,35 @@ def test_assign_dof_errors(solver):
 
 
 @pytest.mark.parametrize("etype", [mesh.HEX8_G2, mesh.HEX8_G1])
-def test_element_stiffness(solver, oracle, etype):
+def test_element_stiffness_bit_exact(solver, oracle, etype):
+    """Element.K_Initial (Element.cs:118-155) through the production integration kernel (k_hex8_ke), BIT-EXACT against
+    the oracle's dense (BL^T D) BL triple loops.  The kernel computes, per node pair, the block whose row node has the
+    smaller DOF index — the only one ParallelAssembly_K uses (col >= row, SolverFunctions.cs:155) — and the API mirrors it.
+    Without a DOF map the local node order decides (all blocks on and above the diagonal are the directly computed
+    ones); with a reversed map most pairs flip, so both K[i][j] and K[j][i] are pinned."""
     m = mesh.beam(4, 3, 5, jitter=True, elem_type=etype, n_parts=2)
     solver.SetModel(m)
-    ke = solver.K_Initial()                                              # Element.cs:118-155
+    ke_up = solver.K_Initial()
+    rev = np.arange(m.n_nodes - 1, -1, -1, dtype=np.int32)
+    solver.SetDOF(rev)
+    ke_rev = solver.K_Initial()
+    r24 = np.arange(24)
+
+    def direct(q):                                                        # entries the kernel computes itself, given the nodes' DOF indices
+        qq = np.repeat(q, 3)
+        return (qq[:, None] < qq[None, :]) | ((qq[:, None] == qq[None, :]) & (r24[:, None] <= r24[None, :]))
+
+    flipped = 0
     for e in range(m.n_elem):
         D = oracle.elastic_D(m.mat_E[m.elem_mat[e]], m.mat_nu[m.elem_mat[e]])
         ref = oracle.k_initial(etype, m.xyz[m.conn[e]], D)
-        assert np.abs(ke[e] - ref).max() <= 1e-13 * np.abs(ref).max()
+        for ke, q in ((ke_up[e], np.arange(8)), (ke_rev[e], rev[m.conn[e]])):
+            M = direct(q)
+            assert np.array_equal(ke[M], ref[M])                          # bit for bit
+            assert np.array_equal(ke, ke.T)                               # the other half is its mirror, as the assembly uses it
+            assert np.abs(ke - ref).max() <= 1e-13 * np.abs(ref).max()    # (the reference's own K is symmetric only to rounding)
+        flipped += int(np.tril(direct(rev[m.conn[e]]), -3).sum())
+    assert flipped > 0                                                    # lower blocks K[j][i], j > i, were exercised
 
 
 def _assembled(solver, oracle, m):
@@ -83,7 +104,8 @@ def test_csr_pattern_bit_exact_values_close(solver, oracle, name):
     rp, col, val = solver.csr_upper()
     orp, ocol, oval = K.arrays()
     assert np.array_equal(rp, orp) and np.array_equal(col, ocol)          # pattern: bit-exact
-    assert np.abs(val - oval).max() <= 1e-12 * np.abs(oval).max()
+    # values: bit-exact too — same Ke arithmetic (no FMA, reference term order), contributions added in ElemLib order
+    assert np.array_equal(val, oval)
 
 
 def test_regular_grid_structural_pattern(solver, oracle):
@@ -92,8 +114,24 @@ def test_regular_grid_structural_pattern(solver, oracle):
     rp, col, val = solver.csr_upper()
     orp, ocol, oval = K.arrays()
     assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
-    # mathematically-zero couplings land on 0.0 or ~1e-12 depending on summation order
-    assert np.abs(val - oval).max() <= 1e-12 * np.abs(oval).max()
+    # mathematically-zero couplings land on 0.0 or ~1e-12 depending on summation order: with the serial
+    # (ElemLib) order on both sides they land on the same bits
+    assert np.array_equal(val, oval)
+    # pruned pattern = what alglib.sparseadd keeps when it meets the elements in this order
+    Kp = oracle.assemble_upper(m, ni, red, prune=True)
+    prp, pcol, pval = Kp.arrays()
+    keep = val != 0.0
+    assert keep.sum() >= Kp.nnz                                          # pruning also drops sums that pass through 0.0
+
+
+def test_assembly_in_row_chunks_is_identical(solver, oracle, monkeypatch):
+    """Meshes whose Ke store does not fit are assembled in row chunks (boundary elements integrated by both)."""
+    m = mesh.beam(5, 4, 9, jitter=True, n_parts=2)
+    ni, red, K = _assembled(solver, oracle, m)
+    one = solver.csr_upper()[2]
+    monkeypatch.setenv("STAN_ASM_CHUNK_ROWS", "37")
+    solver.ParallelAssembly_K()
+    assert np.array_equal(solver.csr_upper()[2], one) and np.array_equal(one, K.arrays()[2])
 
 
 def test_assembly_is_bitwise_deterministic(solver):
@@ -229,9 +267,8 @@ def test_recovery_stress_1e8(solver, oracle):
     solver.Recovery_Stress()
     U = solver.Include_BC_DOF()
     strain, stress = solver.strain_stress()
-    es, ss = oracle.recover(m, ni, U)                                     # same U: isolates R4
-    assert np.abs(strain - es).max() <= 1e-12 * np.abs(es).max()
-    assert np.abs(stress - ss).max() <= 1e-12 * np.abs(ss).max()
+    es, ss = oracle.recover(m, ni, U)                                     # same U: isolates R4 — bit for bit
+    assert np.array_equal(strain, es) and np.array_equal(stress, ss)
     F = oracle.build_rhs(m, ni, red)
     xo, _ = oracle.lincg(K, F, oracle.cg_opts(epsf=1e-10, merit_check=0, maxits=3000))
     es2, ss2 = oracle.recover(m, ni, oracle.include_bc_dof(red, xo))      # end-to-end bar
@@ -247,8 +284,7 @@ def test_recovery_g1_and_patch(solver, oracle):
     U = solver.Include_BC_DOF()
     strain, stress = solver.strain_stress()
     es, ss = oracle.recover(m, ni, U)
-    assert np.abs(strain - es).max() <= 1e-12 * max(np.abs(es).max(), 1e-300)
-    assert np.abs(stress - ss).max() <= 1e-12 * max(np.abs(ss).max(), 1e-300)
+    assert np.array_equal(strain, es) and np.array_equal(stress, ss)
     assert np.abs(strain - strain[:, :1, :]).max() == 0.0                 # every node gets the one Gauss value
 
 
