@@ -37,16 +37,17 @@ k_recover(int64_t e_first, int64_t e_count, const int32_t *__restrict__ conn, co
           const int32_t *__restrict__ elem_list = nullptr) {
     // per element: 8 nodes x (x, y, z, ux, uy, uz); 49-double rows keep the 4 elements of a warp on distinct banks
     __shared__ double s_xu[REC_THREADS / 8][49];
-    // Gauss-point strains (6) and stresses (6); 13-double rows for the same reason
-    __shared__ double s_val[REC_THREADS / 8][8][13];
-    __shared__ double s_tab[9 * 24];               // dN_dLocal: lanes index it by their own Gauss point
+    // Gauss-point strains (6) and stresses (6) in 16-byte aligned rows; 114 doubles per element put the 4 elements
+    // of a warp on distinct banks for the 128-bit extrapolation reads
+    __shared__ __align__(16) double s_val[REC_THREADS / 8][114];
+    __shared__ double s_tab[9 * 25];               // dN_dLocal, 25-double rows: lanes index it by their own Gauss point
     __shared__ double s_N[64];
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t el = t >> 3;                         // local element index
     const int g = (int)(t & 7), le = threadIdx.x >> 3;
     const bool valid = el < e_count;
     const int64_t e = !valid ? 0 : (elem_list ? (int64_t)elem_list[el] : e_first + el);   // global element index
-    if (threadIdx.x < 216) s_tab[threadIdx.x] = (&c_rdNl[0][0])[threadIdx.x];
+    if (threadIdx.x < 216) s_tab[25 * (threadIdx.x / 24) + threadIdx.x % 24] = (&c_rdNl[0][0])[threadIdx.x];
     if (threadIdx.x < 64) s_N[threadIdx.x] = (&c_N[0][0])[threadIdx.x];
     // the 8 threads of an element fetch one node each (coordinates and displacement, Element.cs:214-221)
     int type = STAN_HEX8_G2;
@@ -64,18 +65,23 @@ k_recover(int64_t e_first, int64_t e_count, const int32_t *__restrict__ conn, co
     }
     __syncthreads();
     if (valid && (type == STAN_HEX8_G2 || g == 0)) {
-        const double *tab = s_tab + 24 * ((type == STAN_HEX8_G2) ? g : 8);
+        const double *tab = s_tab + 25 * ((type == STAN_HEX8_G2) ? g : 8);
         const double *X = s_xu[le], *U = s_xu[le] + 24;
-        double J[9];                                   // J = dN_dLocal * X, k ascending (Element.cs:274-292)
+        double J[9];                                   // J = dN_dLocal * X, each entry summed k ascending (Element.cs:274-292)
 #pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                double sum = mul(tab[r * 8], X[c]);
-#pragma unroll
-                for (int k = 1; k < 8; k++) sum = add(sum, mul(tab[r * 8 + k], X[k * 3 + c]));
-                J[r * 3 + c] = sum;
+        for (int k = 0; k < 8; k++) {                  // node by node: 6 shared-memory reads feed 9 products
+            const double t0 = tab[k], t1 = tab[8 + k], t2 = tab[16 + k];
+            const double x0 = X[3 * k], x1 = X[3 * k + 1], x2 = X[3 * k + 2];
+            if (k == 0) {
+                J[0] = mul(t0, x0); J[1] = mul(t0, x1); J[2] = mul(t0, x2);
+                J[3] = mul(t1, x0); J[4] = mul(t1, x1); J[5] = mul(t1, x2);
+                J[6] = mul(t2, x0); J[7] = mul(t2, x1); J[8] = mul(t2, x2);
+            } else {
+                J[0] = add(J[0], mul(t0, x0)); J[1] = add(J[1], mul(t0, x1)); J[2] = add(J[2], mul(t0, x2));
+                J[3] = add(J[3], mul(t1, x0)); J[4] = add(J[4], mul(t1, x1)); J[5] = add(J[5], mul(t1, x2));
+                J[6] = add(J[6], mul(t2, x0)); J[7] = add(J[7], mul(t2, x1)); J[8] = add(J[8], mul(t2, x2));
             }
+        }
         double det = mul(mul(J[0], J[4]), J[8]);       // MatrixST.Det3, MatrixST.cs:274-279
         det = add(det, mul(mul(J[3], J[7]), J[2]));
         det = add(det, mul(mul(J[6], J[1]), J[5]));
@@ -109,7 +115,7 @@ k_recover(int64_t e_first, int64_t e_count, const int32_t *__restrict__ conn, co
             exz = add(exz, mul(dz, ux)); exz = add(exz, mul(dx, uz));
         }
         const double d0 = add(lam, mul(2.0, G));       // Material.cs:42
-        double *v = s_val[le][g];
+        double *v = s_val[le] + 14 * g;
         v[0] = ex; v[1] = ey; v[2] = ez; v[3] = exy; v[4] = eyz; v[5] = exz;
         v[6] = add(add(mul(d0, ex), mul(lam, ey)), mul(lam, ez));      // D.MultiplyVector, Material.cs:42-53
         v[7] = add(add(mul(lam, ex), mul(d0, ey)), mul(lam, ez));
@@ -126,12 +132,17 @@ k_recover(int64_t e_first, int64_t e_count, const int32_t *__restrict__ conn, co
 #pragma unroll
         for (int q = 0; q < 8; q++) {                    // Element.cs:238-245, g ascending
             const double w = s_N[8 * i + q];
+            const double2 *vq = reinterpret_cast<const double2 *>(s_val[le] + 14 * q);
 #pragma unroll
-            for (int c = 0; c < 12; c++) out[c] = add(out[c], mul(s_val[le][q][c], w));
+            for (int c = 0; c < 6; c++) {
+                const double2 v2 = vq[c];
+                out[2 * c] = add(out[2 * c], mul(v2.x, w));
+                out[2 * c + 1] = add(out[2 * c + 1], mul(v2.y, w));
+            }
         }
     } else {
 #pragma unroll
-        for (int c = 0; c < 12; c++) out[c] = s_val[le][0][c];
+        for (int c = 0; c < 12; c++) out[c] = s_val[le][c];
     }
     double *so = strain + el * 48 + i * 6, *to = stress + el * 48 + i * 6;   // Update_StrainStress :257-267
 #pragma unroll
