@@ -71,9 +71,11 @@ template <bool FILL>
 __global__ void k_row_neighbors(int64_t nloc, const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
                                 const int32_t *__restrict__ conn, const int32_t *__restrict__ node_index,
                                 int32_t *__restrict__ cnt, const int32_t *__restrict__ brow_ptr,
-                                int32_t *__restrict__ bcol, int32_t *__restrict__ wide_rows, int32_t *n_wide) {
+                                int32_t *__restrict__ bcol, int32_t *__restrict__ wide_rows, int32_t *n_wide,
+                                const uint8_t *__restrict__ slow_flag) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= nloc) return;
+    if (!slow_flag[p]) return;                        // this row was handled by the warp-per-row kernels
     int32_t nb[ROW_FAST];
     int n = 0;
     bool overflow = false;
@@ -102,6 +104,78 @@ __global__ void k_row_neighbors(int64_t nloc, const int32_t *__restrict__ inc_pt
         int32_t *out = bcol + brow_ptr[p];
         for (int j = 0; j < n; j++) out[j] = nb[j];
     }
+}
+
+// Warp-per-row version of the count pass for rows with at most 8 incident elements (every row of a structured
+// hex mesh): the 64 candidate columns are fetched by 32 lanes at once (three dependent loads in total instead of
+// three per candidate), sorted with a 64-key bitonic network in registers, and the unique ones are written to a
+// 32-column staging row so that the fill pass is a copy.  Rows with more incident elements, or more than 32
+// distinct columns, are flagged in slow[] and left to k_row_neighbors.
+__device__ __forceinline__ void cmp_swap(int32_t &a, int32_t &b, bool up) {
+    const int32_t lo = min(a, b), hi = max(a, b);
+    a = up ? lo : hi; b = up ? hi : lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_row_neighbors_warp(int64_t nloc, const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
+                     const int32_t *__restrict__ conn, const int32_t *__restrict__ node_index,
+                     int32_t *__restrict__ cnt, int32_t *__restrict__ staged, uint8_t *__restrict__ slow) {
+    const int lane = threadIdx.x & 31;
+    const int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (p >= nloc) return;
+    const int t0 = inc_ptr[p], n_ent = inc_ptr[p + 1] - t0;
+    if (n_ent > 8) {
+        if (lane == 0) { cnt[p] = 0; slow[p] = 1; }
+        return;
+    }
+    constexpr int32_t NONE = 0x7fffffff;
+    int32_t a = NONE, b = NONE;                        // keys lane and 32 + lane: entry (lane / 8 [+ 4]), element node lane % 8
+    {
+        const int ta = lane >> 3, k = lane & 7;
+        if (ta < n_ent) a = node_index[conn[8 * (int64_t)(inc[t0 + ta] >> 3) + k]];
+        if (ta + 4 < n_ent) b = node_index[conn[8 * (int64_t)(inc[t0 + ta + 4] >> 3) + k]];
+    }
+    // bitonic sort of 64 keys, ascending; key index = lane for a, 32 + lane for b
+#pragma unroll
+    for (int size = 2; size <= 64; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride == 32) {
+                cmp_swap(a, b, true);                  // size 64: the whole sequence ascending
+            } else {
+                const int32_t oa = __shfl_xor_sync(0xffffffffu, a, stride), ob = __shfl_xor_sync(0xffffffffu, b, stride);
+                const bool lower = (lane & stride) == 0;
+                const bool up_a = (lane & size) == 0 || size == 64, up_b = ((32 + lane) & size) == 0 || size == 64;
+                a = (lower == up_a) ? min(a, oa) : max(a, oa);
+                b = (lower == up_b) ? min(b, ob) : max(b, ob);
+            }
+        }
+    }
+    // unique: a key counts when it differs from its predecessor in sorted order
+    const int32_t pa = __shfl_up_sync(0xffffffffu, a, 1), a31 = __shfl_sync(0xffffffffu, a, 31);
+    int32_t pb = __shfl_up_sync(0xffffffffu, b, 1);
+    if (lane == 0) pb = a31;
+    const bool fa = a != NONE && (lane == 0 || a != pa), fb = b != NONE && b != pb;
+    const unsigned ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
+    const int na = __popc(ma), n = na + __popc(mb);
+    if (n > 32) {
+        if (lane == 0) { cnt[p] = 0; slow[p] = 1; }
+        return;
+    }
+    const unsigned lt = (1u << lane) - 1;
+    if (fa) staged[32 * p + __popc(ma & lt)] = a;
+    if (fb) staged[32 * p + na + __popc(mb & lt)] = b;
+    if (lane == 0) { cnt[p] = n; slow[p] = 0; }
+}
+
+// fill pass for the rows k_row_neighbors_warp staged
+__global__ void k_copy_staged(int64_t nloc, const int32_t *__restrict__ staged, const uint8_t *__restrict__ slow,
+                              const int32_t *__restrict__ brow_ptr, int32_t *__restrict__ bcol) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t p = t >> 5;
+    if (p >= nloc || slow[p]) return;
+    const int j = (int)(t & 31), s0 = brow_ptr[p];
+    if (j < brow_ptr[p + 1] - s0) bcol[s0 + j] = staged[t];
 }
 
 __global__ void k_wide_caps(int n_wide, const int32_t *__restrict__ wide_rows, const int32_t *__restrict__ inc_ptr,
@@ -268,8 +342,15 @@ int build_system_pattern(stan_handle *h) {
     ScratchBuf<int32_t> wide(&h->scratch[2]);            // rows wider than ROW_FAST (none on structured meshes)
     STAN_TRY(wide.alloc(nloc + 1, s));
     int32_t *n_wide_d = h->d_err.p + 6;                  // zeroed with the error flags above
+    // rows with <= 8 incident elements and <= 32 columns: one warp each, staged; the rest: one thread each
+    ScratchBuf<int32_t> staged(&h->scratch[11]);
+    ScratchBuf<uint8_t> slow(&h->scratch[9]);
+    STAN_TRY(staged.alloc((size_t)32 * nloc, s)); STAN_TRY(slow.alloc(nloc, s));
+    k_row_neighbors_warp<<<div_up(32 * nloc, 256), 256, 0, s>>>(nloc, h->d_inc_ptr.p, h->d_inc.p, h->d_conn.p,
+                                                               h->d_node_index.p, cnt.p, staged.p, slow.p);
     k_row_neighbors<false><<<div_up(nloc, 128), 128, 0, s>>>(nloc, h->d_inc_ptr.p, h->d_inc.p, h->d_conn.p,
-                                                             h->d_node_index.p, cnt.p, nullptr, nullptr, wide.p, n_wide_d);
+                                                             h->d_node_index.p, cnt.p, nullptr, nullptr, wide.p, n_wide_d,
+                                                             slow.p);
     STAN_TRY(exclusive_scan(h, cnt.p, h->d_brow_ptr.p, nloc + 1, s));
     int32_t nblk = 0, herr[8];
     STAN_CUDA(cudaMemcpyAsync(&nblk, h->d_brow_ptr.p + nloc, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
@@ -296,16 +377,18 @@ int build_system_pattern(stan_handle *h) {
     }
     h->n_blocks = nblk;
     STAN_TRY(h->d_bcol.alloc((size_t)nblk + 4, s));
+    k_copy_staged<<<div_up(32 * nloc, 256), 256, 0, s>>>(nloc, staged.p, slow.p, h->d_brow_ptr.p, h->d_bcol.p);
     k_row_neighbors<true><<<div_up(nloc, 128), 128, 0, s>>>(nloc, h->d_inc_ptr.p, h->d_inc.p, h->d_conn.p,
                                                             h->d_node_index.p, nullptr, h->d_brow_ptr.p, h->d_bcol.p,
-                                                            nullptr, nullptr);
+                                                            nullptr, nullptr, slow.p);
+    h->launches += 2;
     if (n_wide > 0) {
         k_wide_rows<1><<<div_up(32 * (int64_t)n_wide, 128), 128, 0, s>>>(n_wide, wide.p, woff.p, h->d_inc_ptr.p, h->d_inc.p,
                                                                         h->d_conn.p, h->d_node_index.p, wscr.p, cnt.p,
                                                                         h->d_brow_ptr.p, h->d_bcol.p);
         h->launches += 1;
     }
-    wide.release(s); wcap.release(s); woff.release(s); wscr.release(s);
+    wide.release(s); wcap.release(s); woff.release(s); wscr.release(s); staged.release(s); slow.release(s);
     k_group_max<<<div_up(div_up(nloc, 32), T), T, 0, s>>>(nloc, 32, h->d_brow_ptr.p, h->d_err.p + 1);
     k_group_max<<<div_up(div_up(nloc, 16), T), T, 0, s>>>(nloc, 16, h->d_brow_ptr.p, h->d_err.p + 3);
     cnt.release(s);

@@ -64,6 +64,31 @@ def test_cholesky_agrees_with_cg_and_is_reproducible(oracle):
         assert np.linalg.norm(r) <= 1e-10 * np.linalg.norm(s.F())
 
 
+def test_panel_grid_larger_than_one_wave(monkeypatch):
+    """A block row with more blocks than one resident wave of k_chol_panel CTAs (the later CTAs used to
+    read a diagonal block that CTA 0 had already overwritten with its factor).  56x56 cross-section: half-bandwidth
+    ~9.9 k DOF = 155 blocks; with one block per CTA that is more than the 148 SMs hold at once.  The factorisation
+    is the same arithmetic whatever the grid shape, so the two runs must agree bit for bit, and with CG."""
+    m = mesh.beam(56, 56, 6, tolerance=1e-10)
+    with Solver() as s:
+        s.SetModel(m); s.AssignDOF(); s.ParallelAssembly_K()
+        rep = s.LinearSolver_Cholesky()
+        assert rep.terminationtype == 1
+        x_default = s.Exclude_BC_DOF()
+        monkeypatch.setenv("STAN_CHOL_TILES", "1")
+        rep1 = s.LinearSolver_Cholesky()
+        assert rep1.terminationtype == 1 and rep1.n_blocks == rep.n_blocks
+        x_one = s.Exclude_BC_DOF()
+        assert np.array_equal(x_one, x_default)
+        U = np.zeros(m.n_dof); red = s.nDOF_reduction(); U[red >= 0] = x_one
+        r = s.spmv(U)[red >= 0] - s.F()
+        assert np.linalg.norm(r) <= 1e-9 * np.linalg.norm(s.F())
+        monkeypatch.delenv("STAN_CHOL_TILES")
+        cg = s.LinearSolver_CG(merit_check=0, IterMax=20000)
+        assert cg.terminationtype == 1
+        assert np.linalg.norm(s.Exclude_BC_DOF() - x_one) <= 1e-7 * np.linalg.norm(x_one)
+
+
 def test_not_positive_definite_reports_minus_3_and_zeros(oracle):
     m = mesh.beam(3, 3, 6)
     m.spc_node = m.spc_node[:0]; m.spc_val = m.spc_val[:0]   # rigid-body modes: no Cholesky factor
