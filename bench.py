@@ -312,7 +312,7 @@ def run_ours(args):
             nbytes = r.U_full.nbytes + r.disp.nbytes + r.strain.nbytes + r.stress.nbytes
         return chk, nbytes
 
-    e2e_pass()                                            # untimed: result buffers allocated and touched
+    chk, d2h_rank = e2e_pass()                            # untimed: result buffers allocated and touched
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
@@ -344,7 +344,8 @@ def run_ours(args):
         "metric": METRIC, "value": m.n_elem / (dev_ms * 1e-3), "unit": "elements/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
         "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload, "n_elem": m.n_elem, "n_dof": m.n_dof, "cg": "strict EpsF=1e-8 (merit check off)",
+        "config": {"workload": workload, "n_elem": m.n_elem, "n_dof": m.n_dof,
+                   "cg": "strict EpsF=1e-8 (merit check off)" + (f", CAPPED at {args.cg_maxits} iterations" if args.cg_maxits < 20000 else ""),
                    "parallelism": f"node-range partition x{world}", "l2": "inputs (matrix 72 B/block) far exceed the 126 MB L2",
                    "timing": "CUDA events on the library stream, max over ranks"},
         "breakdown": {"assembly_el_s": m.n_elem / (a.total_ms * 1e-3), "ke_kernel_el_s": m.n_elem / (a.assembly_ms * 1e-3),
@@ -356,7 +357,7 @@ def run_ours(args):
                       "spmv_gbs": achieved_min, "spmv_ms": spmv_ms, "recovery_el_s": m.n_elem / (rc.recover_ms * 1e-3),
                       "recovery_gbs": rc.recover_bytes / (rc.recover_ms * 1e-3) / 1e9, "assign_dof_s": t_dof,
                       "wall_ms_per_step": wall_ms, "call_wall_ms_max_over_ranks": call_ms},
-        "roofline": {"kernel": "k_spmv_tile3 (block-row CSR SpMV + p.Ap" + (", halo exchange fused)" if world > 1 else ")"),
+        "roofline": {"kernel": "k_spmv_tile3 (block-row CSR SpMV + p.Ap)",
                      "bound": "hbm", "achieved": achieved_min, "peak": peak,
                      "unit": "GB/s", "frac": achieved_min / peak, "traffic": traffic, "peak_source": peak_src,
                      "bytes_per_launch": cg.spmv_bytes, "ranks": "minimum over ranks" if world > 1 else "single GPU"},

@@ -12,7 +12,11 @@ from stan_b200.solver import Solver  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "beam_100k_g2"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-m = mesh.workload(name, tolerance=1e-8)
+if name in mesh.WORKLOADS:
+    m = mesh.workload(name, tolerance=1e-8)
+else:                                                 # "nx,ny,nz"
+    f = [int(v) for v in name.split(",")]
+    m = mesh.beam(f[0], f[1], f[2], tolerance=1e-8)
 with Solver() as s:
     s.SetModel(m)
     s.AssignDOF()
