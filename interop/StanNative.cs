@@ -66,6 +66,7 @@ namespace STAN_Solver
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_solve_cholesky(IntPtr h, out CholReport rep);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_recover(IntPtr h, out RecoveryStats st);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_get_displacements(IntPtr h, double[] uFull);
+        [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_get_node_displacements(IntPtr h, double[] disp);
         [DllImport(Lib, CallingConvention = CallingConvention.Cdecl)] internal static extern int stan_get_strain_stress(IntPtr h, double[] strain, double[] stress);
 
         internal static void Check(int rc)
@@ -159,15 +160,15 @@ namespace STAN_Solver
 
                 Console.Write("   Stress recovery: ");                     // Solver.cs:183
                 StanNative.Check(StanNative.stan_recover(h, out _));
-                var U = new double[DB.nDOF];
+                var disp = new double[3 * nodes.Count];                    // Node.dU_buffer per node, NodeLib order
                 var strain = new double[48 * elems.Count];
                 var stress = new double[48 * elems.Count];
-                StanNative.Check(StanNative.stan_get_displacements(h, U));
+                StanNative.Check(StanNative.stan_get_node_displacements(h, disp));
                 StanNative.Check(StanNative.stan_get_strain_stress(h, strain, stress));
                 Console.WriteLine("            Done");
 
-                foreach (var n in nodes)                                   // Solver.cs:171-178
-                    for (int d = 0; d < 3; d++) n.dU_buffer[d] = U[n.DOF[d]];
+                for (int i = 0; i < nodes.Count; i++)                      // Solver.cs:171-178 (the gather ran on the device)
+                    for (int d = 0; d < 3; d++) nodes[i].dU_buffer[d] = disp[3 * i + d];
                 for (int e = 0; e < elems.Count; e++)                      // what Recovery_Stress leaves in dE/dS
                     for (int i = 0; i < 8; i++)
                         for (int c = 0; c < 6; c++)

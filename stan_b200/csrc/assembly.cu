@@ -12,7 +12,7 @@
 //     (BL^T D)[ia][k] is a single product: d_a * (k == a ? lambda + 2G : lambda) for k < 3, d_. * G for the
 //     shear rows; and E[ia][jb] = sum_k (BL^T D)[ia][k] BL[k][jb] has three terms when a == b, two otherwise
 //     (the expressions are written out in block_terms()).
-// Every operation is an explicit __dmul_rn / __dadd_rn (no FMA contraction: the C# JIT and the C oracle
+// Every operation is an explicit __dmul_rn / __dadd_rn (no FMA contraction: the C# JIT and the CPU restatement
 // round after each multiply), so Ke is BIT-IDENTICAL to the dense triple loops — tests/ compares with
 // array_equal — at about a quarter of their operation count.
 //
