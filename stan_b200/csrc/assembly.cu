@@ -95,15 +95,17 @@ __device__ __forceinline__ void block_terms(const double *d, const double *e, do
 // One Gauss point of one element: out[3k + c] = dN_k/dx_c (k = node), out[24] = det J * w.
 // J = dN_dLocal * X with k-ascending sums (MatrixST operator*), J^-1 = adjugate * (1/det) (MatrixST.cs:294-319),
 // dN = J^-1 * dN_dLocal.  Returns false when det J == 0 (the reference throws there).
-__device__ __forceinline__ bool gauss_point_geometry(const double (&X)[24], int gp, double w, double *out) {
+// tab: the 3 x 8 dN_dLocal table of the Gauss point (constant memory, or a shared-memory copy when the lanes of a
+// warp work on different Gauss points and the constant cache would serialise them)
+__device__ __forceinline__ bool gauss_point_geometry(const double (&X)[24], const double *tab, double w, double *out) {
     double J[9];
 #pragma unroll
     for (int r = 0; r < 3; r++)
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            double s = mul(c_dNl[gp][r * 8], X[c]);
+            double s = mul(tab[r * 8], X[c]);
 #pragma unroll
-            for (int k = 1; k < 8; k++) s = add(s, mul(c_dNl[gp][r * 8 + k], X[k * 3 + c]));
+            for (int k = 1; k < 8; k++) s = add(s, mul(tab[r * 8 + k], X[k * 3 + c]));
             J[r * 3 + c] = s;
         }
     const double det = det3(J);
@@ -122,8 +124,7 @@ __device__ __forceinline__ bool gauss_point_geometry(const double (&X)[24], int 
     for (int k = 0; k < 8; k++)
 #pragma unroll
         for (int c = 0; c < 3; c++)
-            out[3 * k + c] = add(add(mul(Ji[c * 3], c_dNl[gp][k]), mul(Ji[c * 3 + 1], c_dNl[gp][8 + k])),
-                                 mul(Ji[c * 3 + 2], c_dNl[gp][16 + k]));
+            out[3 * k + c] = add(add(mul(Ji[c * 3], tab[k]), mul(Ji[c * 3 + 1], tab[8 + k])), mul(Ji[c * 3 + 2], tab[16 + k]));
     out[24] = mul(det, w);
     return det != 0.0;
 }
@@ -168,7 +169,7 @@ k_hex8_ke(int64_t n_local, int64_t first, const int32_t *__restrict__ lelem, con
                 double X[24];
                 load_element(conn, xyz, e, X);
                 // GaussWeight: 1 at the 2x2x2 points, 8 at the centre point (FE_Library.cs:72,100)
-                if (!gauss_point_geometry(X, type == STAN_HEX8_G2 ? g : 8, type == STAN_HEX8_G2 ? 1.0 : 8.0, s_dn[el][g]))
+                if (!gauss_point_geometry(X, c_dNl[type == STAN_HEX8_G2 ? g : 8], type == STAN_HEX8_G2 ? 1.0 : 8.0, s_dn[el][g]))
                     atomicOr(err + 2, 1);
             }
         }
@@ -195,6 +196,90 @@ k_hex8_ke(int64_t n_local, int64_t first, const int32_t *__restrict__ lelem, con
 #pragma unroll
     for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2 *>(out + q) = make_double2(K[q], K[q + 1]);
     *reinterpret_cast<double2 *>(out + 8) = make_double2(K[8], 0.0);
+}
+
+// ---- warp-specialised variant --------------------------------------------------------------------------------
+// ncu on k_hex8_ke: the top stall is the barrier between the phases (9.4 warps per issue) — 224 of 288 threads
+// wait while 64 form the geometry, then those 64 mostly wait.  Here the two phases run concurrently on different
+// warps of a persistent CTA: two producer groups of 64 threads each prepare the geometry of later batches (group
+// it % 2 fills buffer it % 3) while the 288 consumer threads contract the current one; named barriers
+// FULL / EMPTY per buffer replace __syncthreads.  Same arithmetic, same bits.
+constexpr int WS_CONS = KB_THREADS;               // 288 consumer threads = warps 0..8
+constexpr int WS_PROD = 64;                       // per producer group: warps 9,10 and 11,12
+constexpr int WS_THREADS = WS_CONS + 2 * WS_PROD;
+constexpr int WS_BUFS = 3;
+
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+__global__ void __launch_bounds__(WS_THREADS, 2)
+k_hex8_ke_ws(int64_t n_local, int64_t first, const int32_t *__restrict__ lelem, const int32_t *__restrict__ conn,
+             const double *__restrict__ xyz, const int32_t *__restrict__ node_index, const uint8_t *__restrict__ etype,
+             const int32_t *__restrict__ emat, const double *__restrict__ lam_tab, const double *__restrict__ G_tab,
+             double *__restrict__ ke_store, int32_t *__restrict__ qrec, int32_t *err) {
+    __shared__ double s_dn[WS_BUFS][KB_ELEMS][8][25];
+    __shared__ double s_lam[WS_BUFS][KB_ELEMS], s_G[WS_BUFS][KB_ELEMS];
+    __shared__ int s_ng[WS_BUFS][KB_ELEMS];
+    __shared__ int s_q[WS_BUFS][KB_ELEMS][8];
+    __shared__ double s_tab[9 * 25];               // dN_dLocal in 25-double rows: the 8 Gauss points of a producer warp on distinct banks
+    const int tid = threadIdx.x;
+    const int64_t n_batches = (n_local + KB_ELEMS - 1) / KB_ELEMS;
+    constexpr int NB = WS_CONS + WS_PROD;          // participants of every named barrier
+    if (tid < 216) s_tab[25 * (tid / 24) + tid % 24] = (&c_dNl[0][0])[tid];
+    __syncthreads();
+    if (tid >= WS_CONS) {
+        // ---- producers: group g2 prepares iterations g2, g2 + 2, ...
+        const int g2 = (tid - WS_CONS) / WS_PROD, t = (tid - WS_CONS) % WS_PROD;
+        const int el = t >> 3, g = t & 7;
+        for (int64_t it = g2, b = blockIdx.x + (int64_t)g2 * gridDim.x; b < n_batches; it += 2, b += 2 * (int64_t)gridDim.x) {
+            const int buf = (int)(it % WS_BUFS);
+            if (it >= WS_BUFS) named_sync(4 + buf, NB);                // the consumers have released this buffer
+            const int64_t le = b * KB_ELEMS + el;
+            if (le < n_local) {
+                const int64_t e = lelem ? lelem[le] : first + le;
+                const int type = etype[e];
+                const int ng = (type == STAN_HEX8_G2) ? 8 : 1;
+                if (g == 0) { s_ng[buf][el] = ng; const int mat = emat[e]; s_lam[buf][el] = lam_tab[mat]; s_G[buf][el] = G_tab[mat]; }
+                const int q = node_index ? node_index[conn[8 * e + g]] : g;
+                s_q[buf][el][g] = q;
+                qrec[8 * le + g] = q;
+                if (g < ng) {
+                    double X[24];
+                    load_element(conn, xyz, e, X);
+                    if (!gauss_point_geometry(X, s_tab + 25 * (type == STAN_HEX8_G2 ? g : 8), type == STAN_HEX8_G2 ? 1.0 : 8.0, s_dn[buf][el][g]))
+                        atomicOr(err + 2, 1);
+                }
+            } else if (g == 0) s_ng[buf][el] = 0;
+            named_arrive(1 + buf, NB);                                 // buffer full
+        }
+        return;
+    }
+    // ---- consumers
+    const int el = tid / 36, blk = tid - 36 * el;
+    const int bi = c_blk_i[blk], bj = c_blk_j[blk];
+    for (int64_t it = 0, b = blockIdx.x; b < n_batches; it++, b += gridDim.x) {
+        const int buf = (int)(it % WS_BUFS);
+        named_sync(1 + buf, NB);
+        const int ng = s_ng[buf][el];
+        if (ng > 0) {
+            int i = bi, j = bj;
+            if (s_q[buf][el][j] < s_q[buf][el][i]) { const int t = i; i = j; j = t; }
+            const double lam = s_lam[buf][el], G = s_G[buf][el], D0 = add(lam, mul(2.0, G));
+            double K[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) K[q] = 0.0;
+            for (int g = 0; g < ng; g++) {
+                const double *d = s_dn[buf][el][g];
+                block_terms(d + 3 * i, d + 3 * j, lam, G, D0, d[24], K);
+            }
+            double *out = ke_store + ((b * KB_ELEMS + el) * 36 + blk) * KE_BLK;
+#pragma unroll
+            for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2 *>(out + q) = make_double2(K[q], K[q + 1]);
+            *reinterpret_cast<double2 *>(out + 8) = make_double2(K[8], 0.0);
+        }
+        // release the buffer for the producer group that fills it three iterations from now (if there is one)
+        if (b + (int64_t)WS_BUFS * gridDim.x < n_batches) named_arrive(4 + buf, NB);
+    }
 }
 
 constexpr int GA_WARPS = 8;
@@ -346,9 +431,18 @@ int upload_fe_tables() {
 
 static int launch_ke(stan_handle *h, int64_t n_local, int64_t first, const int32_t *lelem, const int32_t *node_index,
                      double *ke_store, int32_t *qrec) {
-    k_hex8_ke<<<div_up(n_local, KB_ELEMS), KB_THREADS, 0, h->stream>>>(n_local, first, lelem, h->d_conn.p, h->d_xyz.p, node_index,
-                                                                       h->d_etype.p, h->d_emat.p, h->d_lambda.p, h->d_G.p,
-                                                                       ke_store, qrec, h->d_err.p);
+    const char *v = getenv("STAN_KE");                 // 0 = two-phase kernel, default = warp-specialised persistent kernel
+    if (v && atoi(v) == 0) {
+        k_hex8_ke<<<div_up(n_local, KB_ELEMS), KB_THREADS, 0, h->stream>>>(n_local, first, lelem, h->d_conn.p, h->d_xyz.p, node_index,
+                                                                           h->d_etype.p, h->d_emat.p, h->d_lambda.p, h->d_G.p,
+                                                                           ke_store, qrec, h->d_err.p);
+    } else {
+        const int64_t nb = div_up(n_local, KB_ELEMS);
+        const int grid = (int)std::min<int64_t>(nb, 2 * (int64_t)h->sm_count);
+        k_hex8_ke_ws<<<grid, WS_THREADS, 0, h->stream>>>(n_local, first, lelem, h->d_conn.p, h->d_xyz.p, node_index,
+                                                         h->d_etype.p, h->d_emat.p, h->d_lambda.p, h->d_G.p, ke_store, qrec,
+                                                         h->d_err.p);
+    }
     STAN_CUDA(cudaGetLastError());
     h->launches += 1;
     return STAN_OK;
