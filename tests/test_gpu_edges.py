@@ -69,3 +69,54 @@ def test_one_handle_many_models(oracle):
             assert np.array_equal(r.node_index, o.node_index)
             if r.cg.terminationtype == 1 and o.stats.cg.terminationtype == 1:
                 assert np.linalg.norm(r.U_full - o.U_full) <= 1e-7 * np.linalg.norm(o.U_full)
+
+
+def test_results_through_every_door(oracle):
+    """U by DOF, U per node (Solver.cs:171-178, gathered on the device), the rows a rank owns, and the same results
+    through page-locked buffers from stan_host_alloc: all the same numbers."""
+    m = mesh.beam(5, 4, 12, jitter=True, n_parts=2, tolerance=1e-9)
+    with Solver() as s, Solver(pinned_results=True) as sp:
+        r = s.SolverLinearStatics(m, merit_check=0)
+        assert np.array_equal(r.disp, r.U_full.reshape(-1, 3)[r.node_index])      # Node.dU_buffer[i] = U_Full[DOF[i]]
+        assert np.array_equal(s.displacements_local().ravel(), r.U_full)          # one GPU owns every row
+        mp = sp.pinned_model(m)
+        rp = sp.SolverLinearStatics(mp, node_index=r.node_index, merit_check=0)
+        for a, b in ((rp.U_full, r.U_full), (rp.disp, r.disp), (rp.strain, r.strain), (rp.stress, r.stress)):
+            assert np.array_equal(a, b)
+        first = rp.stress
+        rp2 = sp.SolverLinearStatics(mp, node_index=r.node_index, merit_check=0)
+        assert rp2.stress is first                                                # pinned result buffers are reused
+
+
+def test_model_checks_run_on_the_device():
+    with Solver() as s:
+        m = mesh.beam(3, 3, 4)
+        bad = mesh.beam(3, 3, 4); bad.conn = bad.conn.copy(); bad.conn[17, 5] = -4
+        with pytest.raises(native.StanError) as ei:
+            s.SetModel(bad)
+        assert ei.value.code == native.E_ARG and "element 17" in str(ei.value) and "-4" in str(ei.value)
+        bad = mesh.beam(3, 3, 4); bad.elem_mat = bad.elem_mat.copy(); bad.elem_mat[20] = -1
+        with pytest.raises(native.StanError) as ei:
+            s.SetModel(bad)
+        assert ei.value.code == native.E_ARG and "element 20" in str(ei.value)
+        s.SetModel(m)
+        with pytest.raises(native.StanError) as ei:                               # a rejected mesh leaves no mesh behind
+            s.SetModel(bad)
+        with pytest.raises(native.StanError) as ei:
+            s.AssignDOF()
+        assert ei.value.code == native.E_STATE
+        s.SetModel(m)
+        ni = s.AssignDOF()
+        dup = ni.copy(); dup[3] = dup[4]
+        with pytest.raises(native.StanError) as ei:
+            s.SetDOF(dup)
+        assert ei.value.code == native.E_ARG and "permutation" in str(ei.value)
+        out = ni.copy(); out[0] = m.n_nodes
+        with pytest.raises(native.StanError) as ei:
+            s.SetDOF(out)
+        assert ei.value.code == native.E_ARG
+        with pytest.raises(native.StanError) as ei:                               # and no DOF map either
+            s.ParallelAssembly_K()
+        assert ei.value.code == native.E_STATE
+        s.SetDOF(ni)
+        assert s.ParallelAssembly_K().n_dof == m.n_dof
