@@ -566,10 +566,10 @@ constexpr int T3_THREADS = 32 * (T3_GROUPS * T3_GW + 1);
 template <bool HALO> struct XArg { typedef const double *__restrict__ type; };   // read-only for the whole kernel
 template <> struct XArg<true> { typedef const double *type; };                      // its halo tail is written by peers
 
-template <bool DOT, bool HALO, bool XPLAIN = HALO>
+template <bool DOT, bool HALO>
 __global__ void __launch_bounds__(T3_THREADS, 1)
 k_spmv_tile3(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t *__restrict__ bcol,
-             const double *__restrict__ vals, typename XArg<XPLAIN>::type x, double *__restrict__ y, BulkLayout L,
+             const double *__restrict__ vals, typename XArg<HALO>::type x, double *__restrict__ y, BulkLayout L,
              double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar, HaloArgs ha) {
     if (st && st->done) return;
     extern __shared__ __align__(128) unsigned char s_raw[];
@@ -805,11 +805,6 @@ k_x_tail(int64_t n, double *__restrict__ x0, double *__restrict__ x1, const doub
         x[i] = x[i] + alpha * p[i];
 }
 
-__global__ void k_scatter_full(int64_t nloc3, const double *__restrict__ x, double *__restrict__ ufull, int64_t dof0) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < nloc3) ufull[dof0 + i] = x[i];
-}
-
 }  // namespace
 
 int64_t spmv_algorithmic_bytes(const stan_handle *h) {
@@ -877,7 +872,6 @@ static int spmv_plan(const stan_handle *h, int64_t nrows, SpmvPlan *p) {
             STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
             STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
             STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
-            STAN_CUDA((cudaFuncSetAttribute(k_spmv_tile3<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem)));
             const int64_t nchunks = (nrows + T3_ROWS - 1) / T3_ROWS;
             p->grid = (int)(nchunks < h->sm_count ? (nchunks > 0 ? nchunks : 1) : h->sm_count);
             return STAN_OK;
@@ -931,11 +925,7 @@ static void launch_spmv(const stan_handle *h, const SpmvPlan &p, bool dot, int64
         nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out, p.L, partials, counter, st, slot, step, run_scalar)
     if (p.variant == 4) {
         const HaloArgs none = {nullptr, nullptr, 0, 0};
-        const char *nc = getenv("STAN_HALO_NC");           // experiment: read-only (ld.global.nc) x loads in the fused kernel
-        if (ha && nc && atoi(nc) == 1)
-            k_spmv_tile3<true, true, false><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
-                                                                               p.L, partials, counter, st, slot, step, run_scalar, *ha);
-        else if (ha)
+        if (ha)
             k_spmv_tile3<true, true><<<p.grid, T3_THREADS, p.smem, s>>>(nrows, h->d_brow_ptr.p, h->bcol_x, h->d_vals.p, in, out,
                                                                         p.L, partials, counter, st, slot, step, run_scalar, *ha);
         else if (dot)
