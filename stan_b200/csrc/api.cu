@@ -18,7 +18,7 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
-void partition_rows(stan_handle *h);   // comm.cu
+int partition_rows(stan_handle *h);   // comm.cu
 
 static int check(stan_handle *h) {
     if (!h) { set_error("null handle"); return STAN_E_ARG; }
@@ -365,7 +365,7 @@ int stan_assemble(stan_handle *h, stan_assembly_stats *stats) {
     cudaStream_t s = h->stream;
     const int64_t launches0 = h->launches;
     h->assembled = h->solved = h->recovered = h->postprocessed = false;
-    partition_rows(h);
+    STAN_TRY(partition_rows(h));
     static const bool trace = getenv("STAN_TRACE") != nullptr;      // host wall clock of the phases, to stderr
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double w0 = now();

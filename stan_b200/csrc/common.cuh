@@ -186,6 +186,7 @@ struct stan_handle {
 
     // ---- partition ----
     int64_t row0 = 0, row1 = 0;         // owned BFS rows [row0, row1)
+    std::vector<int64_t> bounds;        // world + 1 row bounds, the same on every rank (comm.cu: partition_rows)
     int64_t n_halo = 0;                 // halo nodes appended after the owned rows in x vectors
     int64_t nloc_pad = 0;               // node index where the halo tail starts: nloc (1 GPU) or nloc rounded up to HALO_ALIGN
     int64_t elem0 = 0, elem1 = 0;       // elements whose strain/stress this rank recovers

@@ -28,6 +28,20 @@ def test_bounds_cover_all_rows():
         assert np.all((q >= b[own]) & (q < b[own + 1]))
 
 
+def test_weighted_bounds_balance_blocks():
+    from stan_b200 import mesh
+    m = mesh.beam(6, 5, 40)
+    ni = np.arange(m.n_nodes, dtype=np.int32)                     # x-fastest order: slabs along z like the BFS order
+    pairs = partition.node_adjacency(m.conn, ni)
+    blocks = np.bincount(pairs[:, 0], minlength=m.n_nodes)        # stored blocks per row
+    for w in (2, 3, 8):
+        b = partition.weighted_bounds(m.conn, ni, w)
+        assert b[0] == 0 and b[-1] == m.n_nodes and np.all(np.diff(b) > 0)
+        per_rank = np.add.reduceat(blocks, b[:-1])
+        assert per_rank.max() <= 1.05 * per_rank.mean()           # equal node counts would leave the end ranks 3-4 % short
+    assert np.array_equal(partition.weighted_bounds(m.conn, ni, 1), [0, m.n_nodes])
+
+
 def test_gloo_world2_partition_halo_and_reductions():
     r = _torchrun([os.path.join("tests", "dist_worker.py")], 29621)
     assert r.returncode == 0, r.stdout + r.stderr

@@ -26,6 +26,9 @@ dist.broadcast_object_list(uid, src=0)
 multi = Solver(device=local, rank=rank, world=world)
 multi.comm_init(uid[0])
 rm = multi.SolverLinearStatics(m, merit_check=0)
+from stan_b200 import partition  # noqa: E402
+wb = partition.weighted_bounds(m.conn, rm.node_index, world)
+assert multi.partition() == (int(wb[rank]), int(wb[rank + 1])), (multi.partition(), wb)   # host mirror of partition_rows
 single = Solver(device=local)
 rs = single.SolverLinearStatics(m, node_index=rm.node_index, merit_check=0)
 
