@@ -215,7 +215,7 @@ int stan_destroy(stan_handle *h) {
     h->d_b.release(s); h->d_d2.release(s); h->d_err.release(s); h->d_x.release(s); h->d_xalt.release(s);
     h->d_r.release(s); h->d_p.release(s); h->d_mv.release(s); h->d_partials.release(s); h->d_state.release(s);
     h->d_counter.release(s); h->d_ufull.release(s); h->d_strain.release(s); h->d_stress.release(s);
-    h->d_cell.release(s); h->d_point.release(s); h->d_ke.release(s); h->d_hist.release(s);
+    h->d_cell.release(s); h->d_point.release(s); h->d_ke.release(s); h->d_hist.release(s); h->d_trace.release(s);
     for (auto &sl : h->scratch) if (sl.p) cudaFreeAsync(sl.p, s);
     if (h->h_state) cudaFreeHost(h->h_state);
     for (cudaEvent_t e : h->ev_pool) if (e) cudaEventDestroy(e);

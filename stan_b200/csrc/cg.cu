@@ -222,7 +222,9 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double *partials, u
         }
         if (run_scalar && step != SC_NONE) {
             __syncwarp();
+            if (lane == 0) trace_mark(st, step == SC_AFTER_SPMV ? TR_SPMV_LOCAL_DONE : TR_UPDATE_LOCAL_DONE);
             if (st->comm) cross_rank_sum(st, step == SC_AFTER_REFRESH ? 4 : (step == SC_AFTER_SPMV ? 1 : 2), lane);
+            if (lane == 0) trace_mark(st, step == SC_AFTER_SPMV ? TR_SPMV_END : (step == SC_AFTER_REFRESH ? TR_REFRESH_END : TR_UPDATE_END));
             if (lane == 0 && !st->done) scalar_step(st, step);
         }
     }
@@ -572,6 +574,7 @@ k_spmv_tile3(int64_t nrows, const int32_t *__restrict__ brow_ptr, const int32_t 
              const double *__restrict__ vals, typename XArg<HALO>::type x, double *__restrict__ y, BulkLayout L,
              double *partials, unsigned int *counter, CgState *st, int slot, int step, bool run_scalar, HaloArgs ha) {
     if (st && st->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(st, TR_SPMV_BEGIN);
     extern __shared__ __align__(128) unsigned char s_raw[];
     __shared__ __align__(8) uint64_t s_full[T3_GROUPS], s_empty[T3_GROUPS];
     __shared__ double s_part[T3_GROUPS][T3_PARTS][3 * T3_ROWS];
@@ -741,6 +744,7 @@ __global__ void __launch_bounds__(VEC_THREADS)
 k_update(int64_t n, double *__restrict__ r, const double *__restrict__ mv, const double *__restrict__ d2,
          double *partials, unsigned int *counter, CgState *st, bool run_scalar) {
     if (st->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(st, TR_UPDATE_BEGIN);
     const double alpha = st->alpha;
     double v[2] = {0.0, 0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -768,6 +772,7 @@ k_refresh(int64_t n, const double *__restrict__ b, const double *__restrict__ mv
           const double *__restrict__ d2, double *__restrict__ r, double *partials, unsigned int *counter,
           CgState *st, bool run_scalar) {
     if (st->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(st, TR_REFRESH_BEGIN);
     double v[3] = {0.0, 0.0, 0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double ri = b[i] - mv[i];
@@ -782,16 +787,61 @@ k_refresh(int64_t n, const double *__restrict__ b, const double *__restrict__ mv
 
 // x += alpha p (ordinary iterations; a refresh iteration has already installed its candidate x), then
 // p = r d^2 + beta p
-template <bool WITH_X>
+// PUSH (several GPUs, peer-memory mode): the thread that writes a boundary entry of p also stores it into the halo
+// tails of the ranks that read it (per-row send map), the last CTA raises the sequence flags and waits for the
+// neighbours' — the halo exchange of the next product costs no launch of its own (device timeline: the stand-alone
+// push kernel and the kernel boundary around it were 16 of ~530 us per iteration on 8 GPUs).
+template <bool WITH_X, bool PUSH>
 __global__ void __launch_bounds__(VEC_THREADS)
 k_direction(int64_t n, const double *__restrict__ r, const double *__restrict__ d2, double *__restrict__ p,
-            double *__restrict__ x, const CgState *st) {
+            double *__restrict__ x, CgState *st, const CommDev *__restrict__ cd) {
     if (st->done) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) trace_mark(st, TR_DIRECTION_BEGIN);
     const double beta = st->beta, alpha = st->alpha;
+    bool pushed = false;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double pi = p[i];
         if (WITH_X) x[i] = x[i] + alpha * pi;
-        p[i] = r[i] * d2[i] + beta * pi;
+        const double pn = r[i] * d2[i] + beta * pi;
+        p[i] = pn;
+        if (PUSH) {
+            const int64_t node = i / 3;
+            const int c = cd->send_map[node];
+            if (c >= 0) {
+                pushed = true;
+                const int a = (int)(i - 3 * node);
+                for (int e = cd->send_ptr[c]; e < cd->send_ptr[c + 1]; e++) {
+                    const unsigned long long d = cd->send_dst[e];
+                    cd->vec[d >> 48][0][(d & 0xffffffffffffull) + a] = pn;
+                }
+            }
+        }
+    }
+    if (PUSH) {
+        const unsigned long long seq = st->halo_seq + 1;   // (read before any CTA can be last)
+        __shared__ bool last;
+        const bool any_pushed = __syncthreads_or(pushed);
+        if (threadIdx.x == 0) {                            // one fence per CTA that stored remotely, cumulative over its stores
+            if (any_pushed) __threadfence_system();
+            last = (atomicInc(cd->ticket, gridDim.x - 1) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (last && threadIdx.x < 32) {
+            const int W = cd->world, me = cd->rank, lane = threadIdx.x;
+            if (lane == 0) trace_mark(st, TR_PUSH_FLAGS);
+            if (lane < W && lane != me && cd->send_off[lane + 1] > cd->send_off[lane])
+                *(volatile unsigned long long *)&cd->ctrl[lane]->hflag[me] = seq;
+            if (lane < cd->n_recv_peers) {
+                volatile unsigned long long *f = &cd->ctrl[me]->hflag[cd->recv_peer[lane]];
+                const long long t0 = clock64();
+                while (*f < seq) {
+                    if (clock64() - t0 > 8000000000LL) { atomicOr(cd->err + 4, 1); break; }   // ~4 s: a peer died
+                }
+                __threadfence_system();
+            }
+            __syncwarp();
+            if (lane == 0) { st->halo_seq = seq; trace_mark(st, TR_WAIT_END); }
+        }
     }
 }
 
@@ -976,6 +1026,22 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     STAN_TRY(h->d_r.alloc(n, s)); STAN_TRY(h->d_mv.alloc(n, s));
     SpmvPlan plan;
     STAN_TRY(spmv_plan(h, nloc, &plan));
+    if (plan.smem > 0) {
+        // The tile SpMV needs the largest shared-memory carve-out; a kernel with a different preference makes the SM
+        // drain and re-partition L1 / shared memory at every kernel boundary (device timeline, profiles/: 6-9 us
+        // between the kernels of an iteration).  The vector kernels stream and do not miss the L1.
+        const int mx = cudaSharedmemCarveoutMaxShared;
+        cudaFuncSetAttribute(k_update, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_direction<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_direction<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_direction<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_direction<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_candidate, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_refresh, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(k_cg_init, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        comm_prefer_max_shared();
+        (void)cudaGetLastError();
+    }
     const int gv = vec_grid(h, n), gs = plan.grid;
     const int gmax = gv > gs ? gv : gs;
     STAN_TRY(h->d_partials.alloc((size_t)gmax * 4, s));
@@ -1000,6 +1066,14 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
         init.hist = h->d_hist.p;
         init.hist_cap = h->hist_cap;
     }
+    const char *tr_env = getenv("STAN_CG_TRACE");          // profiling aid: device-side timeline of the loop
+    const int tr_cap = tr_env ? atoi(tr_env) : 0;
+    if (tr_cap > 0) {
+        STAN_TRY(h->d_trace.alloc((size_t)2 * tr_cap, s));
+        init.trace = h->d_trace.p;
+        init.trace_cap = tr_cap;
+        init.trace_from = getenv("STAN_CG_TRACE_FROM") ? atoi(getenv("STAN_CG_TRACE_FROM")) : 100;
+    }
     if (!h->h_state) STAN_CUDA(cudaMallocHost((void **)&h->h_state, sizeof(CgState)));
     CgState *hst = h->h_state;
     *hst = init;
@@ -1012,6 +1086,10 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     // and 1 % slower on 8, so the stand-alone kernels are the default.
     const char *fh = getenv("STAN_FUSED_HALO");
     const bool fused_halo = p2p && plan.variant == 4 && fh && atoi(fh) == 1;
+    // STAN_DIR_PUSH=0: stand-alone push / wait launch before every product (A/B timing)
+    const char *dp = getenv("STAN_DIR_PUSH");
+    const bool dir_push = p2p && !fused_halo && !(dp && atoi(dp) == 0);
+    const CommDev *cdp = comm_dev_ptr(h);
     int64_t launches = 0;
     int spmv_launches = 0;
     float spmv_ms = 0.f;
@@ -1031,7 +1109,8 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
         const int vec_id = in == vp ? 0 : (in == vx ? 1 : 2);
         HaloArgs ha;
         const bool fuse = fused_halo && comm_halo_args(h, vec_id, &ha);
-        if (multi && !fuse) STAN_TRY(comm_halo_exchange(h, in, vec_id, s, st));
+        // p's halo was exchanged by the kernel that wrote it (k_direction<.., PUSH>, or the explicit exchange after k_cg_init)
+        if (multi && !fuse && !(dir_push && in == vp)) STAN_TRY(comm_halo_exchange(h, in, vec_id, s, st));
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (timek) {                                       // events come from a grow-only pool kept on the handle
             if (h->ev_pool.size() < evs.size() + 2) {
@@ -1053,6 +1132,7 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
                                          h->d_counter.p, st, single);
     launches++;
     STAN_TRY(reduce_tail(SC_INIT));
+    if (dir_push) STAN_TRY(comm_halo_exchange(h, vp, 0, s, st));   // p of k_cg_init; afterwards k_direction pushes what it writes
 
     // One batch = two refresh periods, so the x / xalt roles are back where they started and every batch
     // is the same launch sequence.  On one GPU without per-launch timing the batch is captured once into
@@ -1082,8 +1162,13 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
                 STAN_TRY(reduce_tail(SC_AFTER_REFRESH));
                 double *t = x; x = xalt; xalt = t;         // accepted unless the state says type 7
             }
-            if (refresh) k_direction<false><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, vp, x, st);
-            else         k_direction<true><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, vp, x, st);
+            if (dir_push) {
+                if (refresh) k_direction<false, true><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, vp, x, st, cdp);
+                else         k_direction<true, true><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, vp, x, st, cdp);
+            } else {
+                if (refresh) k_direction<false, false><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, vp, x, st, nullptr);
+                else         k_direction<true, false><<<gv, VEC_THREADS, 0, s>>>(n, h->d_r.p, h->d_d2.p, vp, x, st, nullptr);
+            }
             launches++;
         }
         return STAN_OK;
@@ -1144,6 +1229,19 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     h->sol = h->x_in_alt ? vxalt : vx;
     h->red_seq = hst->red_seq;
     h->hist_count = hst->k < h->hist_cap ? hst->k : h->hist_cap;
+    if (tr_cap > 0) {                                      // dump: one "ns,iteration,code" line per event
+        const int n_ev = hst->trace_n < tr_cap ? hst->trace_n : tr_cap;
+        std::vector<unsigned long long> ev((size_t)2 * n_ev);
+        if (n_ev) STAN_CUDA(cudaMemcpy(ev.data(), h->d_trace.p, ev.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        const char *dir = getenv("STAN_CG_TRACE_DIR");
+        char path[512];
+        snprintf(path, sizeof path, "%s/stan_cg_trace_rank%d.csv", dir ? dir : ".", h->rank);
+        if (FILE *f = fopen(path, "w")) {
+            for (int i = 0; i < n_ev; i++)
+                fprintf(f, "%llu,%llu,%llu\n", ev[2 * i], ev[2 * i + 1] >> 8, ev[2 * i + 1] & 0xffull);
+            fclose(f);
+        }
+    }
     rep->terminationtype = hst->type;
     rep->iterationscount = hst->k;
     rep->nmv = hst->nmv;

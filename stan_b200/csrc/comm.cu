@@ -78,6 +78,9 @@ struct Comm {
     unsigned long long epoch = 0;          // solves so far: high half of every halo sequence number
     DevBuf<int32_t> d_tile_order;          // SpMV tiles, the ones without halo columns first
     int64_t n_interior = 0;
+    std::vector<int32_t> h_send_rows;      // host copy of d_send_rows (the send map is built from it)
+    DevBuf<int32_t> d_send_map, d_send_ptr;
+    DevBuf<unsigned long long> d_send_dst;
     void *peer_window[P2P_MAX_RANKS] = {};   // IPC mappings of the other ranks' windows
     DevBuf<CommDev> d_dev;
     DevBuf<unsigned int> d_ticket;
@@ -131,6 +134,7 @@ void comm_destroy(stan_handle *h) {
     h->comm->d_sendbuf.release(h->stream);
     h->comm->d_gather.release(h->stream);
     h->comm->d_tile_order.release(h->stream);
+    h->comm->d_send_map.release(h->stream); h->comm->d_send_ptr.release(h->stream); h->comm->d_send_dst.release(h->stream);
     delete h->comm;
     h->comm = nullptr;
 }
@@ -176,23 +180,27 @@ __global__ void k_peer_mask(int64_t nloc, const int32_t *__restrict__ brow_ptr, 
     mask[p] = m;
 }
 
-// Stand-alone halo exchange for the SpMV variants that do not push/wait themselves (rows too wide for the
-// tile kernel): same protocol as the fused kernel.  Push: my boundary entries of window vector `vec_id` go
-// straight into the halo tails of the ranks that read them; the last CTA raises the sequence flags after a
-// system-scope fence.  Every CTA takes a ticket even when the state says done, so the counter stays consistent.
+// Stand-alone halo exchange: the first exchange of a solve, the refresh products (x) and every exchange when
+// k_direction does not push itself (STAN_DIR_PUSH=0, or SpMV variants other than the tile kernel).  Push: my
+// boundary entries of window vector `vec_id` go straight into the halo tails of the ranks that read them; the
+// last CTA raises the sequence flags after a system-scope fence and then waits for the neighbours' flags.  Every
+// CTA takes a ticket even when the state says done, so the counter stays consistent.
 __global__ void __launch_bounds__(256)
-k_halo_push(const CommDev *__restrict__ cd, const double *__restrict__ vec, int vec_id, const CgState *st) {
+k_halo_push(const CommDev *__restrict__ cd, const double *__restrict__ vec, int vec_id, CgState *st) {
     const bool skip = st->done != 0;
+    if (!skip && blockIdx.x == 0 && threadIdx.x == 0) trace_mark(st, TR_PUSH_BEGIN);
     const unsigned long long seq = st->halo_seq + 1;
     const int W = cd->world, me = cd->rank;
     if (!skip) {
-        const long long n3 = 3 * cd->send_off[W];
-        for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n3; t += (long long)gridDim.x * blockDim.x) {
-            const long long i = t / 3;
-            int peer = 0;
-            while (i >= cd->send_off[peer + 1]) peer++;
-            cd->vec[peer][vec_id][cd->tail_off[peer] + 3 * (i - cd->send_off[peer]) + (t - 3 * i)] =
-                vec[3 * (long long)cd->send_rows[i] + (t - 3 * i)];
+        const int32_t *rows = cd->send_rows;
+        for (int peer = 0; peer < W; peer++) {             // one contiguous destination range per peer
+            const long long lo3 = 3 * cd->send_off[peer], hi3 = 3 * cd->send_off[peer + 1];
+            if (hi3 == lo3) continue;
+            double *dst = cd->vec[peer][vec_id] + cd->tail_off[peer] - lo3;
+            for (long long e = lo3 + blockIdx.x * (long long)blockDim.x + threadIdx.x; e < hi3; e += (long long)gridDim.x * blockDim.x) {
+                const long long i = e / 3;
+                dst[e] = vec[3 * (long long)rows[i] + (e - 3 * i)];
+            }
         }
     }
     __shared__ bool last;
@@ -206,24 +214,22 @@ k_halo_push(const CommDev *__restrict__ cd, const double *__restrict__ vec, int 
         __threadfence_system();
         *(volatile unsigned long long *)&cd->ctrl[threadIdx.x]->hflag[me] = seq;
     }
-}
-
-// Halo wait: spin until every source rank has raised its flag for this exchange; the entries are already in
-// the tail of the vector.  One CTA; it also advances the exchange counter of the solve.
-__global__ void __launch_bounds__(32)
-k_halo_wait(const CommDev *__restrict__ cd, CgState *st) {
-    if (st->done) return;
-    const unsigned long long seq = st->halo_seq + 1;
-    if ((int)threadIdx.x < cd->n_recv_peers) {
-        volatile unsigned long long *f = &cd->ctrl[cd->rank]->hflag[cd->recv_peer[threadIdx.x]];
-        const long long t0 = clock64();
-        while (*f < seq) {
-            if (clock64() - t0 > 8000000000LL) { atomicOr(cd->err + 4, 1); break; }   // ~4 s: a peer died
+    if (last && !skip && threadIdx.x == 0) trace_mark(st, TR_PUSH_FLAGS);
+    // The CTA that raised the flags also waits for the neighbours' (they do not depend on this wait: no cycle), so
+    // the exchange is one launch.
+    if (last && !skip && threadIdx.x < 32) {
+        if (threadIdx.x == 0) trace_mark(st, TR_WAIT_BEGIN);
+        if ((int)threadIdx.x < cd->n_recv_peers) {
+            volatile unsigned long long *f = &cd->ctrl[me]->hflag[cd->recv_peer[threadIdx.x]];
+            const long long t0 = clock64();
+            while (*f < seq) {
+                if (clock64() - t0 > 8000000000LL) { atomicOr(cd->err + 4, 1); break; }   // ~4 s: a peer died
+            }
+            __threadfence_system();
         }
-        __threadfence_system();
+        __syncwarp();
+        if (threadIdx.x == 0) { st->halo_seq = seq; trace_mark(st, TR_WAIT_END); }
     }
-    __syncwarp();
-    if (threadIdx.x == 0) st->halo_seq = seq;
 }
 
 __global__ void k_pack(int64_t n_send, const int32_t *__restrict__ rows, const double *__restrict__ vec,
@@ -398,6 +404,29 @@ static int p2p_setup(stan_handle *h) {
     }
     dev.send_off[W] = c->n_send;
     dev.send_rows = c->d_send_rows.p;
+    {   // per-row send map: lets the kernel that writes p store its boundary entries into the peers' tails itself
+        const int64_t nloc = h->row1 - h->row0;
+        std::vector<int32_t> cnt((size_t)nloc, 0), map((size_t)nloc, -1);
+        for (int32_t p : c->h_send_rows) cnt[p]++;
+        std::vector<int32_t> ptr;
+        ptr.push_back(0);
+        for (int64_t p = 0; p < nloc; p++)
+            if (cnt[p]) { map[p] = (int32_t)ptr.size() - 1; ptr.push_back(ptr.back() + cnt[p]); }
+        std::vector<unsigned long long> dst((size_t)ptr.back());
+        std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+        for (int r = 0; r < W; r++)
+            for (int64_t i = c->send_off[r]; i < c->send_off[r] + c->send_cnt[r]; i++) {
+                const int32_t p = c->h_send_rows[i];
+                dst[fill[map[p]]++] = ((unsigned long long)r << 48) | (unsigned long long)(dev.tail_off[r] + 3 * (i - c->send_off[r]));
+            }
+        STAN_TRY(c->d_send_map.alloc(nloc, s)); STAN_TRY(c->d_send_ptr.alloc(ptr.size(), s)); STAN_TRY(c->d_send_dst.alloc(dst.size(), s));
+        STAN_CUDA(cudaMemcpyAsync(c->d_send_map.p, map.data(), nloc * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        STAN_CUDA(cudaMemcpyAsync(c->d_send_ptr.p, ptr.data(), ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        if (!dst.empty())
+            STAN_CUDA(cudaMemcpyAsync(c->d_send_dst.p, dst.data(), dst.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+        STAN_CUDA(cudaStreamSynchronize(s));              // the host vectors go out of scope
+        dev.send_map = c->d_send_map.p; dev.send_ptr = c->d_send_ptr.p; dev.send_dst = c->d_send_dst.p;
+    }
     STAN_TRY(c->d_dev.alloc(1, s));
     if (!c->d_ticket.p) {
         STAN_TRY(c->d_ticket.alloc(1, s));
@@ -467,6 +496,7 @@ int comm_build_halo(stan_handle *h) {
         c->send_cnt[r] = (int64_t)rows.size() - c->send_off[r];
     }
     c->n_send = (int64_t)rows.size();
+    c->h_send_rows = rows;
     STAN_TRY(c->d_send_rows.alloc(rows.size(), s));
     STAN_TRY(c->d_sendbuf.alloc(3 * rows.size(), s));
     if (!rows.empty())
@@ -517,15 +547,20 @@ bool comm_halo_args(const stan_handle *h, int vec_id, HaloArgs *out) {
 
 unsigned long long comm_next_epoch(stan_handle *h) { return h->comm ? ++h->comm->epoch : 0; }
 
+CommDev *comm_dev_ptr(const stan_handle *h) { return comm_p2p_active(h) ? h->comm->d_dev.p : nullptr; }
+
+void comm_prefer_max_shared() {
+    cudaFuncSetAttribute(k_halo_push, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 // vec holds 3*nloc owned entries, padding, and 3*n_halo halo entries from 3*nloc_pad on
 int comm_halo_exchange(stan_handle *h, double *d_vec, int vec_id, cudaStream_t s, CgState *st) {
     if (h->world <= 1) return STAN_OK;
     Comm *c = h->comm;
     if (c->p2p) {
-        const int gp = (int)std::min<int64_t>(std::max<int64_t>(div_up(3 * c->n_send, 256), 1), 64);
-        k_halo_push<<<gp, 256, 0, s>>>(c->d_dev.p, d_vec, vec_id, st);
-        k_halo_wait<<<1, 32, 0, s>>>(c->d_dev.p, st);
-        h->launches += 2;
+        const int gp = (int)std::min<int64_t>(std::max<int64_t>(div_up(3 * c->n_send, 256), 1), 148);
+        k_halo_push<<<gp, 256, 0, s>>>(c->d_dev.p, d_vec, vec_id, st);      // push, raise flags, wait: one launch
+        h->launches += 1;
         return STAN_OK;
     }
     if (c->n_send) {

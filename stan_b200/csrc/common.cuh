@@ -112,6 +112,9 @@ struct CommDev {                                   // device-resident view used 
     long long send_off[P2P_MAX_RANKS + 1];        // my send list grouped by destination rank (nodes)
     long long recv_cnt[P2P_MAX_RANKS];            // halo nodes I receive from rank r
     const int32_t *send_rows;                     // local row of every node to send, grouped by destination
+    const int32_t *send_map;                      // per local row: -1, or c with send_dst[send_ptr[c] .. send_ptr[c+1]) its destinations
+    const int32_t *send_ptr;
+    const unsigned long long *send_dst;           // (peer << 48) | offset in doubles inside the peer's vectors
     unsigned int *ticket;                         // last-CTA detection of the push
     int *err;                                      // device error flags of the handle
 };
@@ -147,8 +150,29 @@ struct CgState {
     unsigned long long halo_seq;  // (solve epoch << 32) | halo exchanges completed in this solve (same on every rank)
     double *hist;     // stan_set_cg_history: rows k = 1.. of {||r_k||^2, alpha_k, beta_k, merit or NaN}, else nullptr
     int32_t hist_cap;
-    int32_t pad0;
+    int32_t trace_from;       // first iteration to trace
+    unsigned long long *trace;    // STAN_CG_TRACE: (globaltimer ns, event code) pairs, else nullptr
+    int32_t trace_cap;
+    int32_t trace_n;
 };
+
+// Device-side timeline of the CG loop (profiling aid, STAN_CG_TRACE=<events>): one thread per kernel stamps
+// %globaltimer at the points that matter for the multi-GPU iteration.  tools/cg_timeline.py reads the dump.
+enum TraceCode { TR_SPMV_BEGIN = 1, TR_SPMV_LOCAL_DONE = 2, TR_SPMV_END = 3, TR_UPDATE_BEGIN = 4, TR_UPDATE_LOCAL_DONE = 5,
+                 TR_UPDATE_END = 6, TR_DIRECTION_BEGIN = 7, TR_PUSH_BEGIN = 8, TR_PUSH_FLAGS = 9, TR_WAIT_BEGIN = 10,
+                 TR_WAIT_END = 11, TR_REFRESH_BEGIN = 12, TR_REFRESH_END = 13 };
+#ifdef __CUDACC__
+__device__ __forceinline__ void trace_mark(CgState *st, int code) {
+    if (!st || !st->trace || st->k < st->trace_from) return;
+    const int i = atomicAdd(&st->trace_n, 1);
+    if (i < st->trace_cap) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        st->trace[2 * i] = t;
+        st->trace[2 * i + 1] = ((unsigned long long)st->k << 8) | (unsigned long long)code;
+    }
+}
+#endif
 
 struct Comm;  // comm.cu
 
@@ -214,6 +238,7 @@ struct stan_handle {
     stan::DevBuf<stan::CgState> d_state;
     stan::DevBuf<unsigned int> d_counter;
     stan::DevBuf<double> d_hist;        // 4 doubles per iteration (stan_set_cg_history)
+    stan::DevBuf<unsigned long long> d_trace;   // STAN_CG_TRACE
     int32_t hist_cap = 0, hist_count = 0;
     bool x_in_alt = false;
     double *sol = nullptr;              // accepted solution of the last solve (owned rows), wherever the solver keeps it
@@ -278,6 +303,8 @@ int comm_halo_exchange(stan_handle *h, double *d_vec, int vec_id, cudaStream_t s
 int comm_cg_vectors(stan_handle *h, double **p, double **x, double **xalt, cudaStream_t s);
 bool comm_halo_args(const stan_handle *h, int vec_id, HaloArgs *out);
 unsigned long long comm_next_epoch(stan_handle *h);
+void comm_prefer_max_shared();
+CommDev *comm_dev_ptr(const stan_handle *h);
 int comm_allgather_rows(stan_handle *h, const double *d_local, double *d_full, cudaStream_t s);
 int comm_build_halo(stan_handle *h);
 bool comm_p2p_active(const stan_handle *h);
