@@ -829,8 +829,11 @@ k_direction(int64_t n, const double *__restrict__ r, const double *__restrict__ 
         if (last && threadIdx.x < 32) {
             const int W = cd->world, me = cd->rank, lane = threadIdx.x;
             if (lane == 0) trace_mark(st, TR_PUSH_FLAGS);
-            if (lane < W && lane != me && cd->send_off[lane + 1] > cd->send_off[lane])
+            if (lane < W && lane != me && cd->send_off[lane + 1] > cd->send_off[lane]) {
+                // acquire side of the ticket (the other CTAs fenced before taking theirs) and release side of the flag
+                __threadfence_system();
                 *(volatile unsigned long long *)&cd->ctrl[lane]->hflag[me] = seq;
+            }
             if (lane < cd->n_recv_peers) {
                 volatile unsigned long long *f = &cd->ctrl[me]->hflag[cd->recv_peer[lane]];
                 const long long t0 = clock64();
