@@ -1029,22 +1029,6 @@ int solve_cg(stan_handle *h, const stan_cg_options *o, stan_cg_report *rep) {
     STAN_TRY(h->d_r.alloc(n, s)); STAN_TRY(h->d_mv.alloc(n, s));
     SpmvPlan plan;
     STAN_TRY(spmv_plan(h, nloc, &plan));
-    if (plan.smem > 0) {
-        // The tile SpMV needs the largest shared-memory carve-out; a kernel with a different preference makes the SM
-        // drain and re-partition L1 / shared memory at every kernel boundary (device timeline, profiles/: 6-9 us
-        // between the kernels of an iteration).  The vector kernels stream and do not miss the L1.
-        const int mx = cudaSharedmemCarveoutMaxShared;
-        cudaFuncSetAttribute(k_update, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_direction<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_direction<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_direction<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_direction<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_candidate, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_refresh, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        cudaFuncSetAttribute(k_cg_init, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        comm_prefer_max_shared();
-        (void)cudaGetLastError();
-    }
     const int gv = vec_grid(h, n), gs = plan.grid;
     const int gmax = gv > gs ? gv : gs;
     STAN_TRY(h->d_partials.alloc((size_t)gmax * 4, s));

@@ -549,10 +549,6 @@ unsigned long long comm_next_epoch(stan_handle *h) { return h->comm ? ++h->comm-
 
 CommDev *comm_dev_ptr(const stan_handle *h) { return comm_p2p_active(h) ? h->comm->d_dev.p : nullptr; }
 
-void comm_prefer_max_shared() {
-    cudaFuncSetAttribute(k_halo_push, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
-
 // vec holds 3*nloc owned entries, padding, and 3*n_halo halo entries from 3*nloc_pad on
 int comm_halo_exchange(stan_handle *h, double *d_vec, int vec_id, cudaStream_t s, CgState *st) {
     if (h->world <= 1) return STAN_OK;

@@ -303,7 +303,6 @@ int comm_halo_exchange(stan_handle *h, double *d_vec, int vec_id, cudaStream_t s
 int comm_cg_vectors(stan_handle *h, double **p, double **x, double **xalt, cudaStream_t s);
 bool comm_halo_args(const stan_handle *h, int vec_id, HaloArgs *out);
 unsigned long long comm_next_epoch(stan_handle *h);
-void comm_prefer_max_shared();
 CommDev *comm_dev_ptr(const stan_handle *h);
 int comm_allgather_rows(stan_handle *h, const double *d_local, double *d_full, cudaStream_t s);
 int comm_build_halo(stan_handle *h);
